@@ -1,0 +1,151 @@
+/*
+ * b200bpe.h — C ABI of libb200bpe.so, the B200 (sm_100a) BPE train/encode hot path.
+ *
+ * The reference (karpathy/minbpe @1acefe8) is pure Python and has no FFI; its hot path is
+ * the three primitives in minbpe/base.py plus the loops in basic.py / regex.py that drive
+ * them.  Every entry point below names the reference lines it replaces.  The Python host
+ * classes in minbpe_b200/tokenizer.py (same names and signatures as minbpe's Tokenizer /
+ * BasicTokenizer / RegexTokenizer) call these through ctypes; INTEGRATION.md shows the stub
+ * a minbpe maintainer would add to bind them.
+ *
+ * Conventions
+ *   - plain pointers and sizes only; no torch / CUDA types cross the boundary.  Pointers are
+ *     HOST pointers unless a parameter is named *_dev (a CUDA device pointer in the handle's
+ *     device, for callers that keep buffers in HBM, e.g. torch.distributed all-reduce glue).
+ *   - every function returns 0 (BPE_OK) or a negative bpe_status; bpe_last_error() gives the
+ *     message.  Nothing throws across the ABI.  No global state besides per-handle state.
+ *   - one handle = one GPU = one host thread at a time.  ctypes releases the GIL during calls.
+ *   - token ids are int32 (the stream is held as 32-bit words in HBM; bit 31 is used
+ *     internally as the "first token of a chunk" mark, so ids must be < 2^31).
+ *   - a "stream" is the token sequence of the whole corpus plus chunk starts.  No pair and no
+ *     merge ever crosses a chunk start (regex.py:51-54,60).  BasicTokenizer = one chunk.
+ */
+#ifndef B200BPE_H
+#define B200BPE_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct bpe_handle bpe_handle;
+
+typedef enum {
+    BPE_OK = 0,
+    BPE_ERR_CUDA = -1,      /* a CUDA runtime call failed (no device, OOM, launch error) */
+    BPE_ERR_ARG = -2,       /* bad argument (NULL, out of range, unsorted offsets) */
+    BPE_ERR_STATE = -3,     /* call order (e.g. train before load_stream) */
+    BPE_ERR_CAPACITY = -4,  /* caller buffer too small; required size is reported */
+    BPE_ERR_INTERNAL = -5
+} bpe_status;
+
+/* ---- lifetime ------------------------------------------------------------------------ */
+
+/* Create a handle bound to CUDA device `device`.  Fails with BPE_ERR_CUDA when there is no
+ * usable sm_100 device: there is NO CPU fallback.  (Stands where the reference constructs a
+ * Tokenizer, base.py:69-74 — the handle is the device-side state of one tokenizer.) */
+int bpe_create(int device, bpe_handle **out);
+int bpe_destroy(bpe_handle *h);
+/* Message for the last failing call on this handle ("" if none).  h may be NULL for a
+ * failed bpe_create. */
+const char *bpe_last_error(const bpe_handle *h);
+/* ABI version of the loaded library (checked by the Python loader). */
+int bpe_abi_version(void);
+
+/* ---- loading a corpus into HBM --------------------------------------------------------- */
+
+/* basic.py:25-26 (`ids = list(text.encode("utf-8"))`) and regex.py:41-44 (`findall` +
+ * per-chunk `list(ch.encode("utf-8"))`): upload `n` text bytes and widen them to the int32
+ * stream in HBM.  chunk_offsets[k] is the byte offset where chunk k starts (strictly
+ * increasing, chunk_offsets[0] == 0); NULL / n_chunks==0 means one chunk (BasicTokenizer). */
+int bpe_load_stream(bpe_handle *h, const uint8_t *bytes, uint64_t n,
+                    const uint64_t *chunk_offsets, uint64_t n_chunks);
+
+/* Same, for an arbitrary id list (what base.py:13 get_stats / base.py:25 merge accept). */
+int bpe_load_ids(bpe_handle *h, const int32_t *ids, uint64_t n,
+                 const uint64_t *chunk_offsets, uint64_t n_chunks);
+
+/* Current stream length in tokens. */
+int bpe_stream_len(bpe_handle *h, uint64_t *n);
+/* Copy the current stream (ids only, chunk marks stripped) to out[0..cap).  *n = length;
+ * BPE_ERR_CAPACITY if cap < *n. */
+int bpe_read_stream(bpe_handle *h, int32_t *out, uint64_t cap, uint64_t *n);
+
+/* ---- the three primitives -------------------------------------------------------------- */
+
+/* base.py:13-22 get_stats(ids): adjacent-pair histogram of the loaded stream, overlaps
+ * counted.  Results in dict insertion order, i.e. sorted by first occurrence in the stream:
+ * pairs[2*i], pairs[2*i+1], counts[i].  *n_pairs = number of distinct pairs;
+ * BPE_ERR_CAPACITY if cap < *n_pairs (call again with a larger buffer). */
+int bpe_get_stats(bpe_handle *h, int32_t *pairs, int64_t *counts, uint64_t cap, uint64_t *n_pairs);
+
+/* base.py:25-41 merge(ids, pair, idx): replace every left-to-right non-overlapping occurrence
+ * of (a, b) in the loaded stream by idx.  *new_len = resulting stream length. */
+int bpe_merge(bpe_handle *h, int32_t a, int32_t b, int32_t idx, uint64_t *new_len);
+
+/* ---- the training loop ----------------------------------------------------------------- */
+
+/* basic.py:31-45 / regex.py:49-66: run up to num_merges iterations of
+ *     stats = get_stats(stream); pair = max(stats, key=stats.get); stream = merge(stream, pair, first_idx+i)
+ * on the loaded stream, entirely on the device.  Ties are broken like the reference: among
+ * the pairs with the highest count, the one whose first occurrence in the current stream is
+ * earliest (dict insertion order, basic.py:35).
+ *   out_pairs[2*i], out_pairs[2*i+1] : pair merged at iteration i (new id first_idx + i)
+ *   out_counts[i]                    : stats[pair] before the merge (the number verbose mode
+ *                                      prints, basic.py:45)
+ *   *n_done                          : iterations completed.  n_done < num_merges means the
+ *                                      stream ran out of pairs, where the reference raises
+ *                                      ValueError (max() of an empty dict, basic.py:35); the
+ *                                      call still returns BPE_OK. */
+int bpe_train(bpe_handle *h, int32_t num_merges, int32_t first_idx,
+              int32_t *out_pairs, int64_t *out_counts, int32_t *n_done);
+
+/* ---- encode ------------------------------------------------------------------------------ */
+
+/* regex.py:92-121 (_encode_chunk per chunk, concatenated: encode_ordinary) and basic.py:57-74
+ * (one chunk): for every chunk, repeatedly merge the present pair with the lowest merge rank.
+ *   merges[2*r], merges[2*r+1] : pair of rank r; its id is 256 + r (base.py:159-165 order)
+ *   byte_perm                  : NULL, or 256 entries mapping a text byte to its initial id
+ *                                (gpt4.py:76-77,90-92)
+ *   out_ids / out_cap / *out_n : caller buffer; n tokens always suffice.
+ * Does not disturb a stream loaded for training. */
+int bpe_encode(bpe_handle *h, const uint8_t *bytes, uint64_t n,
+               const uint64_t *chunk_offsets, uint64_t n_chunks,
+               const int32_t *merges, int32_t n_merges, const uint8_t *byte_perm,
+               int32_t *out_ids, uint64_t out_cap, uint64_t *out_n);
+
+/* ---- measurement --------------------------------------------------------------------------- */
+
+typedef struct {
+    double loop_ms;          /* device time of the last bpe_train merge loop (CUDA events) */
+    double init_ms;          /* device time of the initial histogram + table build */
+    double merge_kernel_ms;  /* summed device time of the fused merge kernel launches when
+                                per-kernel timing is on (BPE_OPT_KERNEL_TIMING), else 0 */
+    uint64_t tokens_in;      /* sum over iterations of the stream length before the merge */
+    uint64_t tokens_out;     /* sum over iterations of the stream length after the merge */
+    uint64_t kernel_launches;/* kernels launched by the last bpe_train / bpe_encode call */
+    uint64_t table_slots;    /* capacity of the pair-count table */
+    uint64_t table_used;     /* occupied slots */
+    uint64_t h2d_bytes;      /* host->device bytes copied by the last load/encode call */
+    uint64_t d2h_bytes;      /* device->host bytes copied by the last train/encode/read call */
+} bpe_timing;
+int bpe_get_timing(bpe_handle *h, bpe_timing *out);
+
+/* Options (bpe_set_option): */
+#define BPE_OPT_KERNEL_TIMING 1 /* 1: bracket each fused-merge launch with CUDA events */
+#define BPE_OPT_RESCAN 2        /* 1: rebuild the histogram from the stream every iteration
+                                   instead of maintaining it incrementally (verification) */
+#define BPE_OPT_BATCH 3         /* max merge iterations enqueued per host synchronisation */
+#define BPE_OPT_TABLE_LOG2 4    /* log2 of the pair-count table capacity (0 = automatic) */
+int bpe_set_option(bpe_handle *h, int opt, int64_t value);
+
+/* Test hook: live entries (count > 0) of the incrementally maintained pair-count table, in no
+ * particular order.  After k merges it must equal get_stats() of the current stream
+ * (tests/test_gpu_parity.py checks exactly that against the oracle). */
+int bpe_debug_table(bpe_handle *h, int32_t *pairs, int64_t *counts, uint64_t cap, uint64_t *n_pairs);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* B200BPE_H */

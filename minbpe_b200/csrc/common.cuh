@@ -1,0 +1,104 @@
+// common.cuh — shared definitions for the sm_100a BPE kernels.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+typedef uint32_t u32;
+typedef uint64_t u64;
+typedef unsigned long long ull;
+
+// ---- token words ---------------------------------------------------------------------------
+// The stream is one 32-bit word per token: bits 0..30 = id, bit 31 = "first token of a chunk".
+// A pair (w[p], w[p+1]) exists iff p+1 < n and w[p+1] has no chunk mark (regex.py:51-54: stats
+// are accumulated chunk by chunk, so no pair spans two chunks).  Comparing w[p+1] against an
+// unmarked id therefore tests "same id AND same chunk" in one instruction.
+#define TOK_FLAG 0x80000000u
+#define TOK_MASK 0x7fffffffu
+#define TOK_SENTINEL 0xffffffffu  // out-of-range filler: marked, id 0x7fffffff never used
+
+// ---- pair-count table ----------------------------------------------------------------------
+#define KEY_EMPTY 0xffffffffffffffffull
+#define POS_NONE 0xffffffffffffffffull
+
+__host__ __device__ __forceinline__ u64 pack_pair(u32 a, u32 b) { return ((u64)a << 32) | (u64)b; }
+
+__host__ __device__ __forceinline__ u64 hash64(u64 x) {
+    x ^= x >> 33; x *= 0xff51afd7ed558ccdull;
+    x ^= x >> 33; x *= 0xc4ceb9fe1a85ec53ull;
+    x ^= x >> 33; return x;
+}
+
+struct Table {
+    u64 *keys;    // [cap]  packed pair or KEY_EMPTY
+    u64 *counts;  // [cap]  occurrences in the current stream (global count when sharded)
+    u64 *first;   // [cap]  first position (only maintained by the full-histogram kernel), may be NULL
+    u64 mask;     // cap - 1
+};
+
+// Find the slot of `key`, inserting it (count 0) if absent.  *inserted counts new slots.
+__device__ __forceinline__ u64 table_upsert(const Table &t, u64 key, ull *used_counter) {
+    u64 slot = hash64(key) & t.mask;
+    for (;;) {
+        u64 k = t.keys[slot];
+        if (k == key) return slot;
+        if (k == KEY_EMPTY) {
+            u64 old = atomicCAS((ull *)&t.keys[slot], (ull)KEY_EMPTY, (ull)key);
+            if (old == KEY_EMPTY) { if (used_counter) atomicAdd(used_counter, 1ull); return slot; }
+            if (old == key) return slot;
+        }
+        slot = (slot + 1) & t.mask;
+    }
+}
+
+// Slot of `key` or POS_NONE.
+__device__ __forceinline__ u64 table_find(const Table &t, u64 key) {
+    u64 slot = hash64(key) & t.mask;
+    for (;;) {
+        u64 k = t.keys[slot];
+        if (k == key) return slot;
+        if (k == KEY_EMPTY) return POS_NONE;
+        slot = (slot + 1) & t.mask;
+    }
+}
+
+// ---- device-resident control block ---------------------------------------------------------
+// Everything the per-iteration kernels need to chain without the host: stream length, which
+// ping-pong buffer is current, the pair selected for the next merge, tickets.
+struct Ctl {
+    u64 n;            // current stream length (tokens)
+    u64 n_next;       // written by the tile that ends the stream during a merge
+    u32 cur;          // index of the ping-pong buffer holding the current stream
+    u32 iter;         // merges completed
+    u32 done;         // 1: no pair left (the reference raises ValueError here)
+    u32 epoch;        // look-back descriptor epoch: +1 per merge launch, never reset (starts at 1)
+    int a, b, z;      // pair selected for merge `iter`, and its new id
+    u32 n_tied;       // number of pairs at the max count
+    u64 best_count;   // max count
+    u64 best_slot;    // a slot holding the max count
+    u64 found_pos;    // find-first result (POS_NONE = not found)
+    ull table_used;   // occupied table slots
+    u32 merge_ticket; // tile dispenser of the merge kernel
+    u32 merge_exit;   // CTAs that left the merge kernel
+    u32 argmax_exit;
+    u32 ff_exit;
+    u64 sum_in, sum_out;  // sum over iterations of n before / after (for GB/s accounting)
+    u32 first_idx;
+    u32 max_iter;     // stop after this many merges
+    u64 reserved[4];
+};
+
+// ---- small helpers -------------------------------------------------------------------------
+__device__ __forceinline__ u64 ld_volatile_u64(const u64 *p) {
+    u64 v;
+    asm volatile("ld.volatile.global.u64 %0, [%1];" : "=l"(v) : "l"(p));
+    return v;
+}
+__device__ __forceinline__ void st_volatile_u64(u64 *p, u64 v) {
+    asm volatile("st.volatile.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+__device__ __forceinline__ u32 ld_volatile_u32(const u32 *p) {
+    u32 v;
+    asm volatile("ld.volatile.global.u32 %0, [%1];" : "=r"(v) : "l"(p));
+    return v;
+}
+__device__ __forceinline__ u32 lane_id() { return threadIdx.x & 31; }

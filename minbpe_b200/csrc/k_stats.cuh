@@ -1,0 +1,281 @@
+// k_stats.cuh — pair statistics: full histograms (get_stats, base.py:13-22), the device-wide
+// arg-max with the reference's first-occurrence tie-break (basic.py:35 / regex.py:56), and the
+// incremental table update that follows a merge.
+#pragma once
+#include "common.cuh"
+
+// =============================================================================================
+// Full histogram of a BYTE stream (all ids < 256) into a dense 256x256 vector.
+// One pass, 4 tokens per thread per step (16-byte loads), warp-level de-duplication of equal
+// keys before the global reduction.  Used once per train() (iteration 0) — afterwards the table
+// is maintained incrementally by the merge kernel.  dense[p0*256+p1] += count.
+// =============================================================================================
+__global__ void __launch_bounds__(256) k_hist_dense(const u32 *__restrict__ buf0, const u32 *__restrict__ buf1,
+                                                    const Ctl *__restrict__ ctl, ull *__restrict__ dense,
+                                                    u32 *__restrict__ err) {
+    const u32 *__restrict__ w = ctl->cur ? buf1 : buf0;
+    const u64 n = ctl->n;
+    const u64 nvec = (n + 3) / 4;
+    for (u64 v = (u64)blockIdx.x * blockDim.x + threadIdx.x; v < nvec; v += (u64)gridDim.x * blockDim.x) {
+        const u64 p0 = v * 4;
+        u32 t[5];
+        if (p0 + 4 <= n) {
+            uint4 q = *reinterpret_cast<const uint4 *>(w + p0);
+            t[0] = q.x; t[1] = q.y; t[2] = q.z; t[3] = q.w;
+        } else {
+#pragma unroll
+            for (int k = 0; k < 4; ++k) t[k] = (p0 + k < n) ? w[p0 + k] : TOK_SENTINEL;
+        }
+        t[4] = (p0 + 4 < n) ? w[p0 + 4] : TOK_SENTINEL;
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            const u32 left = t[k] & TOK_MASK, right = t[k + 1];
+            const bool valid = (p0 + k < n) && !(right & TOK_FLAG);
+            if (valid && (left > 255u || right > 255u)) *err = 1;
+            const u32 key = valid ? ((left & 255u) << 8 | (right & 255u)) : 0xffffffffu;
+            // lanes with the same key elect one leader that adds the whole group
+            const u32 peers = __match_any_sync(__activemask(), key);
+            if (valid && (__ffs(peers) - 1) == (int)lane_id()) atomicAdd(&dense[key], (ull)__popc(peers));
+        }
+    }
+}
+
+// dense 256x256 vector -> table entries (one thread per bin)
+__global__ void k_dense_to_table(const ull *__restrict__ dense, Table t, Ctl *ctl) {
+    const u32 i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= 65536u) return;
+    const ull c = dense[i];
+    if (!c) return;
+    const u64 slot = table_upsert(t, pack_pair(i >> 8, i & 255u), &ctl->table_used);
+    t.counts[slot] = c;
+}
+
+// =============================================================================================
+// Full histogram of an arbitrary stream into the hash table, with first-occurrence positions
+// (count += 1, first = min(first, p)).  This is get_stats() for the C ABI and the "rescan"
+// verification mode.  Same scan shape as k_hist_dense.
+// =============================================================================================
+__global__ void __launch_bounds__(256) k_hist_hash(const u32 *__restrict__ buf0, const u32 *__restrict__ buf1,
+                                                   Ctl *ctl, Table t, int gated) {
+    if (gated && (ctl->done || ctl->iter >= ctl->max_iter)) return;
+    const u32 *__restrict__ w = ctl->cur ? buf1 : buf0;
+    const u64 n = ctl->n;
+    const u64 nvec = (n + 3) / 4;
+    for (u64 v = (u64)blockIdx.x * blockDim.x + threadIdx.x; v < nvec; v += (u64)gridDim.x * blockDim.x) {
+        const u64 p0 = v * 4;
+        u32 tk[5];
+        if (p0 + 4 <= n) {
+            uint4 q = *reinterpret_cast<const uint4 *>(w + p0);
+            tk[0] = q.x; tk[1] = q.y; tk[2] = q.z; tk[3] = q.w;
+        } else {
+#pragma unroll
+            for (int k = 0; k < 4; ++k) tk[k] = (p0 + k < n) ? w[p0 + k] : TOK_SENTINEL;
+        }
+        tk[4] = (p0 + 4 < n) ? w[p0 + 4] : TOK_SENTINEL;
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            const bool valid = (p0 + k < n) && !(tk[k + 1] & TOK_FLAG);
+            const u64 key = valid ? pack_pair(tk[k] & TOK_MASK, tk[k + 1]) : KEY_EMPTY;
+            const u32 peers = __match_any_sync(__activemask(), key);
+            // the lowest lane of a group also holds the group's smallest position
+            if (valid && (__ffs(peers) - 1) == (int)lane_id()) {
+                const u64 slot = table_upsert(t, key, &ctl->table_used);
+                atomicAdd((ull *)&t.counts[slot], (ull)__popc(peers));
+                if (t.first) atomicMin((ull *)&t.first[slot], (ull)(p0 + k));
+            }
+        }
+    }
+}
+
+// =============================================================================================
+// Arg-max over the table: max count, how many pairs share it, one slot holding it.
+// Two-level: per-thread -> warp shuffle -> block -> last block (ticket) reduces the partials.
+// When the max is unique the winning pair is final; otherwise k_find_first resolves the tie by
+// stream position, which is what the reference's dict insertion order amounts to.
+// =============================================================================================
+struct Best { u64 count; u64 slot; u32 tied; };
+
+__device__ __forceinline__ Best best_combine(Best x, Best y) {
+    if (y.count > x.count) return y;
+    if (y.count == x.count) { x.tied += y.tied; if (y.slot < x.slot) x.slot = y.slot; }
+    return x;
+}
+
+__device__ __forceinline__ Best best_warp_reduce(Best v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        Best y;
+        y.count = __shfl_xor_sync(0xffffffffu, v.count, o);
+        y.slot = __shfl_xor_sync(0xffffffffu, v.slot, o);
+        y.tied = __shfl_xor_sync(0xffffffffu, v.tied, o);
+        v = best_combine(v, y);
+    }
+    return v;
+}
+
+// log layout: pairs int32[2*i], counts int64[i]
+__device__ __forceinline__ void record_selection(Ctl *ctl, int a, int b, u64 count, int *log_pairs, long long *log_counts) {
+    ctl->a = a; ctl->b = b; ctl->z = (int)(ctl->first_idx + ctl->iter);
+    if (log_pairs) { log_pairs[2 * ctl->iter] = a; log_pairs[2 * ctl->iter + 1] = b; log_counts[ctl->iter] = (long long)count; }
+}
+
+__global__ void __launch_bounds__(256) k_argmax(Table t, Ctl *ctl, Best *partials, int *log_pairs, long long *log_counts) {
+    if (ctl->done || ctl->iter >= ctl->max_iter) return;
+    const u64 cap = t.mask + 1;
+    Best v; v.count = 0; v.slot = POS_NONE; v.tied = 0;
+    // two 64-bit counts per 16-byte load
+    const ulonglong2 *c2 = reinterpret_cast<const ulonglong2 *>(t.counts);
+    for (u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x; i < cap / 2; i += (u64)gridDim.x * blockDim.x) {
+        ulonglong2 c = c2[i];
+        if (c.x) { Best y; y.count = c.x; y.slot = 2 * i; y.tied = 1; v = best_combine(v, y); }
+        if (c.y) { Best y; y.count = c.y; y.slot = 2 * i + 1; y.tied = 1; v = best_combine(v, y); }
+    }
+    v = best_warp_reduce(v);
+    __shared__ Best s[8];
+    __shared__ bool last;
+    if (lane_id() == 0) s[threadIdx.x >> 5] = v;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        for (int k = 1; k < (int)(blockDim.x >> 5); ++k) v = best_combine(v, s[k]);
+        partials[blockIdx.x] = v;
+        __threadfence();
+        last = (atomicAdd(&ctl->argmax_exit, 1u) == gridDim.x - 1);
+    }
+    __syncthreads();
+    if (!last) return;
+    __threadfence();
+    // last block: reduce the per-block partials
+    Best r; r.count = 0; r.slot = POS_NONE; r.tied = 0;
+    for (u32 k = threadIdx.x; k < gridDim.x; k += blockDim.x) {
+        Best y;
+        y.count = ld_volatile_u64(&partials[k].count);
+        y.slot = ld_volatile_u64(&partials[k].slot);
+        y.tied = ld_volatile_u32(&partials[k].tied);
+        r = best_combine(r, y);
+    }
+    r = best_warp_reduce(r);
+    if (lane_id() == 0) s[threadIdx.x >> 5] = r;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        for (int k = 1; k < (int)(blockDim.x >> 5); ++k) r = best_combine(r, s[k]);
+        ctl->argmax_exit = 0;
+        ctl->best_count = r.count; ctl->best_slot = r.slot; ctl->n_tied = r.tied;
+        ctl->found_pos = POS_NONE;
+        if (r.count == 0) ctl->done = 1;                    // max({}) -> ValueError in the reference
+        else if (r.tied == 1) {
+            const u64 key = t.keys[r.slot];
+            record_selection(ctl, (int)(key >> 32), (int)(key & 0xffffffffu), r.count, log_pairs, log_counts);
+        }
+    }
+}
+
+// =============================================================================================
+// Tie-break: among the pairs whose count equals the max, the reference picks the one inserted
+// first into the dict = the one whose first occurrence in the current stream is earliest.
+// Scan the stream from the front in tiles, look each pair up, stop at the first tile that holds a
+// hit (later tiles exit as soon as they see found_pos in front of them).  Expected cost is
+// n / (tied * count) tokens — a tiny prefix unless counts are ~1.
+// =============================================================================================
+#define FF_TILE 2048
+__global__ void __launch_bounds__(256) k_find_first(const u32 *__restrict__ buf0, const u32 *__restrict__ buf1,
+                                                    Table t, Ctl *ctl, int *log_pairs, long long *log_counts) {
+    if (ctl->done || ctl->iter >= ctl->max_iter || ctl->n_tied <= 1) return;
+    const u32 *w = ctl->cur ? buf1 : buf0;
+    const u64 n = ctl->n, best = ctl->best_count;
+    __shared__ bool last;
+    __shared__ u64 s_found;
+    for (u64 tile = blockIdx.x;; tile += gridDim.x) {
+        const u64 base = tile * FF_TILE;
+        if (threadIdx.x == 0) s_found = ld_volatile_u64(&ctl->found_pos);
+        __syncthreads();
+        if (base >= n || s_found < base) break;  // block-uniform: a hit in front of this tile ends the scan
+        u64 hit = POS_NONE;
+        for (u32 j = threadIdx.x; j < FF_TILE; j += blockDim.x) {
+            const u64 p = base + j;
+            if (p + 1 < n) {
+                const u32 right = w[p + 1];
+                if (!(right & TOK_FLAG)) {
+                    const u64 slot = table_find(t, pack_pair(w[p] & TOK_MASK, right));
+                    if (slot != POS_NONE && t.counts[slot] == best) { hit = p; break; }  // ascending j: first hit of this thread
+                }
+            }
+        }
+        if (hit != POS_NONE) atomicMin((ull *)&ctl->found_pos, (ull)hit);
+        __syncthreads();
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) { __threadfence(); last = (atomicAdd(&ctl->ff_exit, 1u) == gridDim.x - 1); }
+    __syncthreads();
+    if (last && threadIdx.x == 0) {
+        __threadfence();
+        ctl->ff_exit = 0;
+        const u64 p = ld_volatile_u64(&ctl->found_pos);
+        if (p == POS_NONE) ctl->done = 1;  // cannot happen when the table matches the stream
+        else record_selection(ctl, (int)(w[p] & TOK_MASK), (int)w[p + 1], best, log_pairs, log_counts);
+    }
+}
+
+// =============================================================================================
+// Incremental update of the table after merging (a,b) -> z.  The merge kernel leaves, per token
+// id x, L[x] = number of merges whose left neighbour is an unmerged x, R[x] = number of merges
+// whose right neighbour is an unmerged x, and ZZ = number of merges directly followed by another
+// merge.  Then (DESIGN.md "Incremental statistics"):
+//     count(x,a) -= L[x]   count(x,z) = L[x]
+//     count(b,x) -= R[x]   count(z,x) = R[x]
+//     count(b,a) -= ZZ     count(z,z) = ZZ         count(a,b) = 0
+// delta layout: [0,V) = L, [V,2V) = R, [2V] = ZZ, V = vocab capacity.  The vector is zeroed.
+// =============================================================================================
+__device__ __forceinline__ void table_sub(const Table &t, u64 key, u64 skip_key, ull d) {
+    if (key == skip_key) return;  // (a,b) itself is zeroed wholesale
+    const u64 slot = table_find(t, key);
+    if (slot != POS_NONE) atomicAdd((ull *)&t.counts[slot], (ull)(0ull - d));
+}
+
+__global__ void __launch_bounds__(256) k_apply_delta(Table t, Ctl *ctl, ull *__restrict__ delta, u32 V,
+                                                     int a_arg, int b_arg, int z_arg, int use_ctl) {
+    if (use_ctl && (ctl->done || ctl->iter > ctl->max_iter)) return;
+    const u32 a = use_ctl ? (u32)ctl->a : (u32)a_arg, b = use_ctl ? (u32)ctl->b : (u32)b_arg,
+              z = use_ctl ? (u32)ctl->z : (u32)z_arg;
+    const u64 kab = pack_pair(a, b);
+    const u32 x = blockIdx.x * blockDim.x + threadIdx.x;
+    if (x < V) {
+        const ull l = delta[x];
+        if (l) {
+            delta[x] = 0;
+            table_sub(t, pack_pair(x, a), kab, l);
+            const u64 s = table_upsert(t, pack_pair(x, z), &ctl->table_used);
+            atomicAdd((ull *)&t.counts[s], l);
+        }
+        const ull r = delta[V + x];
+        if (r) {
+            delta[V + x] = 0;
+            table_sub(t, pack_pair(b, x), kab, r);
+            const u64 s = table_upsert(t, pack_pair(z, x), &ctl->table_used);
+            atomicAdd((ull *)&t.counts[s], r);
+        }
+    }
+    if (x == 0) {
+        const ull zz = delta[2 * (u64)V];
+        if (zz) {
+            delta[2 * (u64)V] = 0;
+            table_sub(t, pack_pair(b, a), kab, zz);
+            const u64 s = table_upsert(t, pack_pair(z, z), &ctl->table_used);
+            atomicAdd((ull *)&t.counts[s], zz);
+        }
+        const u64 s = table_find(t, kab);
+        if (s != POS_NONE) t.counts[s] = 0;
+    }
+}
+
+// Copy live entries (count > 0) into a fresh table (growth / dropping dead pairs).
+__global__ void k_rehash(Table src, Table dst, Ctl *ctl) {
+    const u64 cap = src.mask + 1;
+    for (u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x; i < cap; i += (u64)gridDim.x * blockDim.x) {
+        const u64 k = src.keys[i];
+        const u64 c = src.counts[i];
+        if (k != KEY_EMPTY && c) {
+            const u64 s = table_upsert(dst, k, &ctl->table_used);
+            dst.counts[s] = c;
+        }
+    }
+}

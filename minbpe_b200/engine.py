@@ -1,0 +1,194 @@
+"""
+ctypes binding of libb200bpe.so (include/b200bpe.h) — the only door between the Python host
+classes and the sm_100a kernels.  There is NO CPU fallback: if the library is missing or no
+B200 is present, every operation raises.
+"""
+import ctypes
+import os
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "csrc", "libb200bpe.so")
+ABI_VERSION = 1
+
+OPT_KERNEL_TIMING, OPT_RESCAN, OPT_BATCH, OPT_TABLE_LOG2 = 1, 2, 3, 4
+ERR_CAPACITY = -4
+
+_lib = None
+
+
+class EngineError(RuntimeError):
+    pass
+
+
+class Timing(ctypes.Structure):
+    _fields_ = [("loop_ms", ctypes.c_double), ("init_ms", ctypes.c_double), ("merge_kernel_ms", ctypes.c_double),
+                ("tokens_in", ctypes.c_uint64), ("tokens_out", ctypes.c_uint64), ("kernel_launches", ctypes.c_uint64),
+                ("table_slots", ctypes.c_uint64), ("table_used", ctypes.c_uint64), ("h2d_bytes", ctypes.c_uint64),
+                ("d2h_bytes", ctypes.c_uint64)]
+
+    def as_dict(self):
+        return {k: getattr(self, k) for k, _ in self._fields_}
+
+
+def load_library():
+    """Load libb200bpe.so and declare every entry point of include/b200bpe.h."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise EngineError(f"{LIB_PATH} not found: build it with `python minbpe_b200/csrc/build.py` "
+                          "(minbpe_b200 has no CPU fallback)")
+    L = ctypes.CDLL(LIB_PATH)
+    vp, u64, i32, i64, ci = ctypes.c_void_p, ctypes.c_uint64, ctypes.c_int32, ctypes.c_int64, ctypes.c_int
+    P = ctypes.POINTER
+    sig = {
+        "bpe_abi_version": ([], ci),
+        "bpe_create": ([ci, P(vp)], ci),
+        "bpe_destroy": ([vp], ci),
+        "bpe_last_error": ([vp], ctypes.c_char_p),
+        "bpe_load_stream": ([vp, vp, u64, vp, u64], ci),
+        "bpe_load_ids": ([vp, vp, u64, vp, u64], ci),
+        "bpe_stream_len": ([vp, P(u64)], ci),
+        "bpe_read_stream": ([vp, vp, u64, P(u64)], ci),
+        "bpe_get_stats": ([vp, vp, vp, u64, P(u64)], ci),
+        "bpe_merge": ([vp, i32, i32, i32, P(u64)], ci),
+        "bpe_train": ([vp, i32, i32, vp, vp, P(i32)], ci),
+        "bpe_encode": ([vp, vp, u64, vp, u64, vp, i32, vp, vp, u64, P(u64)], ci),
+        "bpe_get_timing": ([vp, P(Timing)], ci),
+        "bpe_set_option": ([vp, ci, i64], ci),
+        "bpe_debug_table": ([vp, vp, vp, u64, P(u64)], ci),
+    }
+    for name, (args, res) in sig.items():
+        fn = getattr(L, name)  # AttributeError here = header/library mismatch
+        fn.argtypes, fn.restype = args, res
+    if L.bpe_abi_version() != ABI_VERSION:
+        raise EngineError(f"libb200bpe ABI {L.bpe_abi_version()} != expected {ABI_VERSION}")
+    _lib = L
+    return L
+
+
+def _ptr(a):
+    return None if a is None else ctypes.c_void_p(a.ctypes.data)
+
+
+def _as_offsets(offs):
+    if offs is None:
+        return None, 0
+    o = np.ascontiguousarray(offs, dtype=np.uint64)
+    return o, int(o.size)
+
+
+class Engine:
+    """One handle = one GPU = device-side state of one tokenizer (stream + pair table)."""
+
+    def __init__(self, device=None):
+        self._lib = load_library()
+        if device is None:
+            device = int(os.environ.get("LOCAL_RANK", "0")) if os.environ.get("BPE_DEVICE") is None else int(os.environ["BPE_DEVICE"])
+        h = ctypes.c_void_p()
+        rc = self._lib.bpe_create(int(device), ctypes.byref(h))
+        if rc != 0:
+            raise EngineError(f"bpe_create(device={device}) failed ({rc}): {self._lib.bpe_last_error(None).decode()}")
+        self._h = h
+        self.device = int(device)
+
+    def close(self):
+        if getattr(self, "_h", None):
+            self._lib.bpe_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:  # noqa: BLE001
+            pass
+
+    def _check(self, rc, what):
+        if rc != 0:
+            raise EngineError(f"{what} failed ({rc}): {self._lib.bpe_last_error(self._h).decode()}")
+
+    # ---- corpus ----
+    def load_stream(self, data, offsets=None):
+        b = np.frombuffer(data, dtype=np.uint8) if not isinstance(data, np.ndarray) else np.ascontiguousarray(data, dtype=np.uint8)
+        o, k = _as_offsets(offsets)
+        self._keep = (b, o)
+        self._check(self._lib.bpe_load_stream(self._h, _ptr(b) if b.size else None, b.size, _ptr(o), k), "bpe_load_stream")
+
+    def load_ids(self, ids, offsets=None):
+        a = np.ascontiguousarray(ids, dtype=np.int32)
+        o, k = _as_offsets(offsets)
+        self._check(self._lib.bpe_load_ids(self._h, _ptr(a) if a.size else None, a.size, _ptr(o), k), "bpe_load_ids")
+
+    def stream_len(self):
+        n = ctypes.c_uint64()
+        self._check(self._lib.bpe_stream_len(self._h, ctypes.byref(n)), "bpe_stream_len")
+        return n.value
+
+    def read_stream(self):
+        n = self.stream_len()
+        out = np.empty(max(n, 1), dtype=np.int32)
+        got = ctypes.c_uint64()
+        self._check(self._lib.bpe_read_stream(self._h, _ptr(out), out.size, ctypes.byref(got)), "bpe_read_stream")
+        return out[: got.value]
+
+    # ---- primitives ----
+    def get_stats(self):
+        """-> (pairs[k,2] int32, counts[k] int64) in first-occurrence (dict insertion) order."""
+        cap = max(self.stream_len(), 1)
+        pairs = np.empty((cap, 2), dtype=np.int32)
+        counts = np.empty(cap, dtype=np.int64)
+        n = ctypes.c_uint64()
+        self._check(self._lib.bpe_get_stats(self._h, _ptr(pairs), _ptr(counts), cap, ctypes.byref(n)), "bpe_get_stats")
+        return pairs[: n.value], counts[: n.value]
+
+    def merge(self, a, b, idx):
+        n = ctypes.c_uint64()
+        self._check(self._lib.bpe_merge(self._h, int(a), int(b), int(idx), ctypes.byref(n)), "bpe_merge")
+        return n.value
+
+    def train(self, num_merges, first_idx=256):
+        """-> (pairs[k,2], counts[k], n_done); n_done < num_merges means the stream ran out of pairs."""
+        pairs = np.zeros((max(num_merges, 1), 2), dtype=np.int32)
+        counts = np.zeros(max(num_merges, 1), dtype=np.int64)
+        done = ctypes.c_int32()
+        self._check(self._lib.bpe_train(self._h, int(num_merges), int(first_idx), _ptr(pairs), _ptr(counts),
+                                        ctypes.byref(done)), "bpe_train")
+        return pairs[: done.value], counts[: done.value], done.value
+
+    def encode(self, data, offsets, merges, byte_perm=None):
+        """-> ids int32.  merges: [M,2] int32 in rank order (id of rank r = 256 + r)."""
+        b = np.frombuffer(data, dtype=np.uint8) if not isinstance(data, np.ndarray) else np.ascontiguousarray(data, dtype=np.uint8)
+        o, k = _as_offsets(offsets)
+        m = np.ascontiguousarray(np.asarray(merges, dtype=np.int32).reshape(-1, 2))
+        perm = None if byte_perm is None else np.ascontiguousarray(byte_perm, dtype=np.uint8)
+        out = np.empty(max(b.size, 1), dtype=np.int32)
+        n = ctypes.c_uint64()
+        self._check(self._lib.bpe_encode(self._h, _ptr(b) if b.size else None, b.size, _ptr(o), k,
+                                         _ptr(m) if m.size else None, m.shape[0], _ptr(perm), _ptr(out), out.size,
+                                         ctypes.byref(n)), "bpe_encode")
+        return out[: n.value]
+
+    # ---- measurement / options ----
+    def timing(self):
+        t = Timing()
+        self._check(self._lib.bpe_get_timing(self._h, ctypes.byref(t)), "bpe_get_timing")
+        return t.as_dict()
+
+    def set_option(self, opt, value):
+        self._check(self._lib.bpe_set_option(self._h, int(opt), int(value)), "bpe_set_option")
+
+    def debug_table(self):
+        """Live entries of the incremental pair table: dict pair -> count (test hook)."""
+        cap = 1 << 16
+        while True:
+            pairs = np.empty((cap, 2), dtype=np.int32)
+            counts = np.empty(cap, dtype=np.int64)
+            n = ctypes.c_uint64()
+            rc = self._lib.bpe_debug_table(self._h, _ptr(pairs), _ptr(counts), cap, ctypes.byref(n))
+            if rc == ERR_CAPACITY:
+                cap = int(n.value) + 16
+                continue
+            self._check(rc, "bpe_debug_table")
+            return {(int(p[0]), int(p[1])): int(c) for p, c in zip(pairs[: n.value], counts[: n.value])}
