@@ -14,6 +14,7 @@
 #include "common.cuh"
 #include "k_load.cuh"
 #include "k_merge.cuh"
+#include "k_merge_fast.cuh"
 #include "k_stats.cuh"
 #include "k_encode.cuh"
 
@@ -42,10 +43,10 @@ struct bpe_handle {
     u32 *d_err = nullptr;
     int *log_pairs = nullptr; long long *log_counts = nullptr; int log_cap = 0;
     Best *partials = nullptr;
-    int argmax_grid = 0, merge_grid = 0, merge_grid_same = 0, ff_grid = 0;
+    int argmax_grid = 0, merge_grid = 0, merge_grid_same = 0, merge_grid_fast = 0, ff_grid = 0;
 
     // options
-    int opt_kernel_timing = 0, opt_rescan = 0, opt_batch = 256, opt_table_log2 = 0;
+    int opt_kernel_timing = 0, opt_rescan = 0, opt_batch = 256, opt_table_log2 = 0, opt_merge_impl = 1;
 
     bpe_timing tm = {};
     std::vector<cudaEvent_t> ev_pool;  // per-launch timing of the fused merge kernel (BPE_OPT_KERNEL_TIMING)
@@ -140,6 +141,12 @@ extern "C" int bpe_create(int device, bpe_handle **out) {
     if (occ_same < 1) occ_same = 1;
     h->merge_grid = h->sms * occ;
     h->merge_grid_same = h->sms * occ_same;
+    int occ_fast = 0;
+    if ((e = cudaFuncSetAttribute(k_merge_fast, cudaFuncAttributeMaxDynamicSharedMemorySize, MF_SMEM_BYTES)) != cudaSuccess)
+        return bail("cudaFuncSetAttribute(k_merge_fast)", e);
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_fast, k_merge_fast, MF_THREADS, MF_SMEM_BYTES);
+    if (occ_fast < 1) return bail("k_merge_fast does not fit on an SM", cudaErrorLaunchOutOfResources);
+    h->merge_grid_fast = h->sms * occ_fast;
     h->argmax_grid = h->sms * 2;
     h->ff_grid = h->sms * 4;
     if ((e = cudaMalloc(&h->partials, sizeof(Best) * h->argmax_grid)) != cudaSuccess) return bail("cudaMalloc partials", e);
@@ -181,6 +188,7 @@ extern "C" int bpe_set_option(bpe_handle *h, int opt, int64_t value) {
         case BPE_OPT_TABLE_LOG2:
             if (value != 0 && (value < 10 || value > 30)) return fail(h, BPE_ERR_ARG, "table log2 must be 0 or in [10,30]");
             h->opt_table_log2 = (int)value; break;
+        case BPE_OPT_MERGE_IMPL: h->opt_merge_impl = (int)value; break;
         default: return fail(h, BPE_ERR_ARG, "unknown option");
     }
     return BPE_OK;
@@ -405,7 +413,8 @@ extern "C" int bpe_get_stats(bpe_handle *h, int32_t *pairs, int64_t *counts, uin
 static void launch_merge(bpe_handle *h, ull *delta, int force) {
     MergeArgs A;
     A.ctl = h->ctl; A.buf0 = h->buf[0]; A.buf1 = h->buf[1]; A.desc = h->desc; A.delta = delta; A.V = h->V; A.force = force;
-    k_merge<false><<<h->merge_grid, MG_THREADS, 0, h->stream>>>(A);
+    if (h->opt_merge_impl == 1) k_merge_fast<<<h->merge_grid_fast, MF_THREADS, MF_SMEM_BYTES, h->stream>>>(A);
+    else k_merge<false><<<h->merge_grid, MG_THREADS, 0, h->stream>>>(A);
     k_merge<true><<<h->merge_grid_same, MG_THREADS, 0, h->stream>>>(A);
     h->tm.kernel_launches += 2;
 }

@@ -102,3 +102,34 @@ __device__ __forceinline__ u32 ld_volatile_u32(const u32 *p) {
     return v;
 }
 __device__ __forceinline__ u32 lane_id() { return threadIdx.x & 31; }
+
+// ---- mbarrier + bulk async copy (TMA 1-D) — hand-written PTX for sm_100a ---------------------
+__device__ __forceinline__ u32 smem_addr(const void *p) { return (u32)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(u64 *bar, u32 count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_addr(bar)), "r"(count) : "memory");
+}
+// make mbarrier initialisation visible to the async proxy before the first bulk copy targets it
+__device__ __forceinline__ void fence_mbar_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+
+__device__ __forceinline__ void mbar_arrive_expect_tx(u64 *bar, u32 tx_bytes) {
+    u64 state;
+    asm volatile("mbarrier.arrive.expect_tx.release.cta.shared::cta.b64 %0, [%1], %2;"
+                 : "=l"(state) : "r"(smem_addr(bar)), "r"(tx_bytes) : "memory");
+    (void)state;
+}
+__device__ __forceinline__ bool mbar_try_wait(u64 *bar, u32 parity) {
+    u32 ok;
+    asm volatile("{\n\t.reg .pred P;\n\t"
+                 "mbarrier.try_wait.parity.shared::cta.b64 P, [%1], %2;\n\t"
+                 "selp.b32 %0, 1, 0, P;\n\t}"
+                 : "=r"(ok) : "r"(smem_addr(bar)), "r"(parity) : "memory");
+    return ok != 0;
+}
+__device__ __forceinline__ void mbar_wait(u64 *bar, u32 parity) { while (!mbar_try_wait(bar, parity)) {} }
+
+// global -> shared bulk copy (SASS: UBLKCP); bytes, src and dst must be multiples of 16
+__device__ __forceinline__ void bulk_g2s(void *dst_smem, const void *src_gmem, u32 bytes, u64 *bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(smem_addr(dst_smem)), "l"(src_gmem), "r"(bytes), "r"(smem_addr(bar)) : "memory");
+}

@@ -12,7 +12,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "csrc", "libb200bpe.so")
 ABI_VERSION = 1
 
-OPT_KERNEL_TIMING, OPT_RESCAN, OPT_BATCH, OPT_TABLE_LOG2 = 1, 2, 3, 4
+OPT_KERNEL_TIMING, OPT_RESCAN, OPT_BATCH, OPT_TABLE_LOG2, OPT_MERGE_IMPL = 1, 2, 3, 4, 5
 ERR_CAPACITY = -4
 
 _lib = None
