@@ -14,7 +14,8 @@
 #include "common.cuh"
 #include "k_load.cuh"
 #include "k_merge.cuh"
-#include "k_merge_fast.cuh"
+#include "k_merge_seg.cuh"
+#include "k_seg.cuh"
 #include "k_stats.cuh"
 #include "k_encode.cuh"
 
@@ -38,12 +39,13 @@ struct bpe_handle {
     Table table = {nullptr, nullptr, nullptr, 0};
     bool table_valid = false;  // table == get_stats(current stream)
     u64 *desc = nullptr; u64 desc_cap = 0;
+    Edge *edge[2] = {nullptr, nullptr}; u64 *seg_offs = nullptr; u64 seg_cap = 0;  // segmented stream metadata
     ull *delta = nullptr; u32 V = 0;
     ull *dense = nullptr;
     u32 *d_err = nullptr;
     int *log_pairs = nullptr; long long *log_counts = nullptr; int log_cap = 0;
     Best *partials = nullptr;
-    int argmax_grid = 0, merge_grid = 0, merge_grid_same = 0, merge_grid_fast = 0, ff_grid = 0;
+    int argmax_grid = 0, merge_grid = 0, merge_grid_same = 0, merge_grid_seg = 0, ff_grid = 0;
 
     // options
     int opt_kernel_timing = 0, opt_rescan = 0, opt_batch = 256, opt_table_log2 = 0, opt_merge_impl = 1;
@@ -142,11 +144,11 @@ extern "C" int bpe_create(int device, bpe_handle **out) {
     h->merge_grid = h->sms * occ;
     h->merge_grid_same = h->sms * occ_same;
     int occ_fast = 0;
-    if ((e = cudaFuncSetAttribute(k_merge_fast, cudaFuncAttributeMaxDynamicSharedMemorySize, MF_SMEM_BYTES)) != cudaSuccess)
-        return bail("cudaFuncSetAttribute(k_merge_fast)", e);
-    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_fast, k_merge_fast, MF_THREADS, MF_SMEM_BYTES);
-    if (occ_fast < 1) return bail("k_merge_fast does not fit on an SM", cudaErrorLaunchOutOfResources);
-    h->merge_grid_fast = h->sms * occ_fast;
+    if ((e = cudaFuncSetAttribute(k_merge_seg, cudaFuncAttributeMaxDynamicSharedMemorySize, MS_SMEM_BYTES)) != cudaSuccess)
+        return bail("cudaFuncSetAttribute(k_merge_seg)", e);
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_fast, k_merge_seg, MS_THREADS, MS_SMEM_BYTES);
+    if (occ_fast < 1) return bail("k_merge_seg does not fit on an SM", cudaErrorLaunchOutOfResources);
+    h->merge_grid_seg = h->sms * occ_fast;
     h->argmax_grid = h->sms * 2;
     h->ff_grid = h->sms * 4;
     if ((e = cudaMalloc(&h->partials, sizeof(Best) * h->argmax_grid)) != cudaSuccess) return bail("cudaMalloc partials", e);
@@ -166,6 +168,8 @@ extern "C" int bpe_destroy(bpe_handle *h) {
     for (cudaEvent_t e : h->ev_pool) cudaEventDestroy(e);
     free_table(h, h->table);
     if (h->desc) cudaFree(h->desc);
+    for (int i = 0; i < 2; ++i) if (h->edge[i]) cudaFree(h->edge[i]);
+    if (h->seg_offs) cudaFree(h->seg_offs);
     if (h->delta) cudaFree(h->delta);
     if (h->dense) cudaFree(h->dense);
     if (h->d_err) cudaFree(h->d_err);
@@ -188,7 +192,7 @@ extern "C" int bpe_set_option(bpe_handle *h, int opt, int64_t value) {
         case BPE_OPT_TABLE_LOG2:
             if (value != 0 && (value < 10 || value > 30)) return fail(h, BPE_ERR_ARG, "table log2 must be 0 or in [10,30]");
             h->opt_table_log2 = (int)value; break;
-        case BPE_OPT_MERGE_IMPL: h->opt_merge_impl = (int)value; break;
+        case BPE_OPT_MERGE_IMPL: h->opt_merge_impl = (int)value; break;  /* kept for ABI compatibility; unused */
         default: return fail(h, BPE_ERR_ARG, "unknown option");
     }
     return BPE_OK;
@@ -219,7 +223,35 @@ static int ensure_stream_capacity(bpe_handle *h, u64 n) {
         CU(cudaMemsetAsync(h->desc, 0, tiles * 8, h->stream));
         h->desc_cap = tiles;
     }
+    const u64 segs = need / SEG_TOKENS + 1;
+    if (segs > h->seg_cap) {
+        for (int i = 0; i < 2; ++i) { if (h->edge[i]) cudaFree(h->edge[i]); h->edge[i] = nullptr; }
+        if (h->seg_offs) cudaFree(h->seg_offs);
+        h->seg_offs = nullptr; h->seg_cap = 0;
+        for (int i = 0; i < 2; ++i) CU(cudaMalloc(&h->edge[i], segs * sizeof(Edge)));
+        CU(cudaMalloc(&h->seg_offs, segs * 8));
+        h->seg_cap = segs;
+    }
     return BPE_OK;
+}
+
+// edge records for a stream that was just written contiguously into the current buffer
+static int build_edges(bpe_handle *h, u64 n) {
+    const u64 nseg = (n + SEG_TOKENS - 1) / SEG_TOKENS;
+    k_build_edges<<<grid_for(nseg, 256, h->sms * 4), 256, 0, h->stream>>>(h->buf[0], h->buf[1], h->ctl, h->edge[0], 0);
+    CU(cudaGetLastError());
+    return BPE_OK;
+}
+
+// pack the segmented stream back into full segments (other ping-pong buffer becomes current)
+static void enqueue_pack(bpe_handle *h, int force) {
+    k_scan_counts<<<1, 1024, 0, h->stream>>>(h->ctl, h->edge[0], h->edge[1], h->seg_offs, force);
+    k_gather<<<h->sms * 8, 256, 0, h->stream>>>(h->ctl, h->buf[0], h->buf[1], h->edge[0], h->edge[1], h->seg_offs, nullptr, force, 1);
+    h->tm.kernel_launches += 2;
+}
+static void enqueue_edges_after_contig(bpe_handle *h) {
+    k_build_edges<<<h->sms * 4, 256, 0, h->stream>>>(h->buf[0], h->buf[1], h->ctl, h->edge[0], 1);
+    h->tm.kernel_launches += 1;
 }
 
 static int push_ctl(bpe_handle *h) {
@@ -307,6 +339,7 @@ extern "C" int bpe_load_stream(bpe_handle *h, const uint8_t *bytes, uint64_t n, 
     if ((rc = load_bytes_into(h, h->buf[0], bytes, n, nullptr))) return rc;
     if ((rc = mark_chunks(h, h->buf[0], chunk_offsets, n_chunks, n))) return rc;
     if ((rc = reset_ctl_for_stream(h, n))) return rc;
+    if ((rc = build_edges(h, n))) return rc;
     h->loaded = true; h->bytes_only = true;
     return BPE_OK;
 }
@@ -335,6 +368,7 @@ extern "C" int bpe_load_ids(bpe_handle *h, const int32_t *ids, uint64_t n, const
     }
     if ((rc = mark_chunks(h, h->buf[0], chunk_offsets, n_chunks, n))) return rc;
     if ((rc = reset_ctl_for_stream(h, n))) return rc;
+    if ((rc = build_edges(h, n))) return rc;
     h->loaded = true; h->bytes_only = false;
     return BPE_OK;
 }
@@ -361,8 +395,12 @@ extern "C" int bpe_read_stream(bpe_handle *h, int32_t *out, uint64_t cap, uint64
     if (len == 0) return BPE_OK;
     if (!out) return fail(h, BPE_ERR_ARG, "out is NULL");
     const u32 cur = h->h_ctl->cur;
-    // strip marks into the idle ping-pong buffer, then copy out
-    k_strip_flags<<<grid_for(len, 256, h->sms * 8), 256, 0, h->stream>>>(h->buf[cur], (int *)h->buf[cur ^ 1], len);
+    // pack the segments into the idle ping-pong buffer (the stream itself stays as it is), strip
+    // the chunk marks there, copy out
+    k_scan_counts<<<1, 1024, 0, h->stream>>>(h->ctl, h->edge[0], h->edge[1], h->seg_offs, 1);
+    k_gather<<<h->sms * 8, 256, 0, h->stream>>>(h->ctl, h->buf[0], h->buf[1], h->edge[0], h->edge[1], h->seg_offs,
+                                                 h->buf[cur ^ 1], 1, 0);
+    k_strip_flags<<<grid_for(len, 256, h->sms * 8), 256, 0, h->stream>>>(h->buf[cur ^ 1], (int *)h->buf[cur ^ 1], len);
     CU(cudaMemcpyAsync(out, h->buf[cur ^ 1], len * 4, cudaMemcpyDeviceToHost, h->stream));
     CU(cudaStreamSynchronize(h->stream));
     h->tm.d2h_bytes = len * 4;
@@ -383,7 +421,7 @@ extern "C" int bpe_get_stats(bpe_handle *h, int32_t *pairs, int64_t *counts, uin
     Table t;
     if ((rc = alloc_table(h, t, tcap, true))) { free_table(h, t); return rc; }
     const u64 used_before = h->h_ctl->table_used;
-    k_hist_hash<<<grid_for((n + 3) / 4, 256, h->sms * 8), 256, 0, h->stream>>>(h->buf[0], h->buf[1], h->ctl, t, 0);
+    k_hist_hash<<<h->sms * 8, 256, 0, h->stream>>>(h->buf[0], h->buf[1], h->ctl, h->edge[0], h->edge[1], t, 0);
     std::vector<u64> keys(tcap), cnt(tcap), first(tcap);
     cudaError_t e = cudaMemcpyAsync(keys.data(), t.keys, tcap * 8, cudaMemcpyDeviceToHost, h->stream);
     if (e == cudaSuccess) e = cudaMemcpyAsync(cnt.data(), t.counts, tcap * 8, cudaMemcpyDeviceToHost, h->stream);
@@ -410,13 +448,27 @@ extern "C" int bpe_get_stats(bpe_handle *h, int32_t *pairs, int64_t *counts, uin
 
 // ------------------------------------------------------------------------------------------------
 // merge (base.py:25-41), single step
-static void launch_merge(bpe_handle *h, ull *delta, int force) {
-    MergeArgs A;
-    A.ctl = h->ctl; A.buf0 = h->buf[0]; A.buf1 = h->buf[1]; A.desc = h->desc; A.delta = delta; A.V = h->V; A.force = force;
-    if (h->opt_merge_impl == 1) k_merge_fast<<<h->merge_grid_fast, MF_THREADS, MF_SMEM_BYTES, h->stream>>>(A);
-    else k_merge<false><<<h->merge_grid, MG_THREADS, 0, h->stream>>>(A);
-    k_merge<true><<<h->merge_grid_same, MG_THREADS, 0, h->stream>>>(A);
-    h->tm.kernel_launches += 2;
+// One merge over the stream.  Pairs a != b: the segmented in-place pass.  Pairs (a,a) need the
+// run-parity carry along the stream, so they pack the stream and use the contiguous kernel
+// (which also refills every segment).  Every kernel gates itself on the device-resident pair, so
+// the whole sequence is enqueued unconditionally; `same` >= 0 lets the host skip the no-ops when
+// it knows the pair (single-step API).
+static void launch_merge(bpe_handle *h, ull *delta, int force, int same = -1) {
+    if (same != 1) {
+        SegArgs S;
+        S.ctl = h->ctl; S.buf0 = h->buf[0]; S.buf1 = h->buf[1]; S.e0 = h->edge[0]; S.e1 = h->edge[1];
+        S.delta = delta; S.V = h->V; S.force = force;
+        k_merge_seg<<<h->merge_grid_seg, MS_THREADS, MS_SMEM_BYTES, h->stream>>>(S);
+        h->tm.kernel_launches += 1;
+    }
+    if (same != 0) {
+        MergeArgs A;
+        A.ctl = h->ctl; A.buf0 = h->buf[0]; A.buf1 = h->buf[1]; A.desc = h->desc; A.delta = delta; A.V = h->V; A.force = force;
+        enqueue_pack(h, force);
+        k_merge<true><<<h->merge_grid_same, MG_THREADS, 0, h->stream>>>(A);
+        h->tm.kernel_launches += 1;
+        enqueue_edges_after_contig(h);
+    }
 }
 
 extern "C" int bpe_merge(bpe_handle *h, int32_t a, int32_t b, int32_t idx, uint64_t *new_len) {
@@ -429,7 +481,7 @@ extern "C" int bpe_merge(bpe_handle *h, int32_t a, int32_t b, int32_t idx, uint6
     if (rc) return rc;
     h->h_ctl->a = a; h->h_ctl->b = b; h->h_ctl->z = idx;
     if ((rc = push_ctl(h))) return rc;
-    launch_merge(h, nullptr, 1);
+    launch_merge(h, nullptr, 1, a == b ? 1 : 0);
     CU(cudaGetLastError());
     if ((rc = pull_ctl(h))) return rc;
     h->table_valid = false;
@@ -474,11 +526,11 @@ static int build_table(bpe_handle *h, u64 cap) {
     if (h->bytes_only) {
         CU(cudaMemsetAsync(h->dense, 0, 65536 * 8, h->stream));
         CU(cudaMemsetAsync(h->d_err, 0, 4, h->stream));
-        k_hist_dense<<<grid_for((n + 3) / 4, 256, h->sms * 8), 256, 0, h->stream>>>(h->buf[0], h->buf[1], h->ctl, h->dense, h->d_err);
+        k_hist_dense<<<h->sms * 8, 256, 0, h->stream>>>(h->buf[0], h->buf[1], h->ctl, h->edge[0], h->edge[1], h->dense, h->d_err);
         k_dense_to_table<<<65536 / 256, 256, 0, h->stream>>>(h->dense, h->table, h->ctl);
         h->tm.kernel_launches += 2;
     } else {
-        k_hist_hash<<<grid_for((n + 3) / 4, 256, h->sms * 8), 256, 0, h->stream>>>(h->buf[0], h->buf[1], h->ctl, h->table, 0);
+        k_hist_hash<<<h->sms * 8, 256, 0, h->stream>>>(h->buf[0], h->buf[1], h->ctl, h->edge[0], h->edge[1], h->table, 0);
         h->tm.kernel_launches += 1;
     }
     CU(cudaGetLastError());
@@ -519,16 +571,26 @@ static void timed_merge(bpe_handle *h, ull *delta) {
     h->ev_used += 2;
 }
 
+// Between batches: when merges have emptied the segments below half full on average, pack the
+// stream into full segments again (fewer, fuller segments = less per-segment overhead).
+static void maybe_repack(bpe_handle *h) {
+    const u64 nseg = h->h_ctl->nseg;
+    if (nseg < 64 || h->h_ctl->contig) return;
+    if (2 * h->h_ctl->n >= nseg * (u64)SEG_TOKENS) return;
+    enqueue_pack(h, 1);
+    enqueue_edges_after_contig(h);
+}
+
 static void enqueue_iteration(bpe_handle *h) {
     if (h->opt_rescan) {
         // verification mode: rebuild the histogram from the stream, no incremental update
         cudaMemsetAsync(h->table.keys, 0xff, (h->table.mask + 1) * 8, h->stream);
         cudaMemsetAsync(h->table.counts, 0, (h->table.mask + 1) * 8, h->stream);
-        k_hist_hash<<<h->sms * 8, 256, 0, h->stream>>>(h->buf[0], h->buf[1], h->ctl, h->table, 1);
+        k_hist_hash<<<h->sms * 8, 256, 0, h->stream>>>(h->buf[0], h->buf[1], h->ctl, h->edge[0], h->edge[1], h->table, 1);
         h->tm.kernel_launches++;
     }
     k_argmax<<<h->argmax_grid, 256, 0, h->stream>>>(h->table, h->ctl, h->partials, h->log_pairs, h->log_counts);
-    k_find_first<<<h->ff_grid, 256, 0, h->stream>>>(h->buf[0], h->buf[1], h->table, h->ctl, h->log_pairs, h->log_counts);
+    k_find_first<<<h->ff_grid, 256, 0, h->stream>>>(h->buf[0], h->buf[1], h->edge[0], h->edge[1], h->table, h->ctl, h->log_pairs, h->log_counts);
     h->tm.kernel_launches += 2;
     if (h->opt_rescan) timed_merge(h, nullptr);
     else {
@@ -601,6 +663,7 @@ extern "C" int bpe_train(bpe_handle *h, int32_t num_merges, int32_t first_idx, i
             continue;
         }
         k = std::min(k, num_merges - done_iters);
+        maybe_repack(h);
         for (int i = 0; i < k; ++i) enqueue_iteration(h);
         CU(cudaGetLastError());
         if ((rc = pull_ctl(h))) return rc;

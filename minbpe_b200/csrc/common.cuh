@@ -84,7 +84,29 @@ struct Ctl {
     u64 sum_in, sum_out;  // sum over iterations of n before / after (for GB/s accounting)
     u32 first_idx;
     u32 max_iter;     // stop after this many merges
-    u64 reserved[4];
+    // segmented stream (DESIGN.md "Stream layout"): nseg segments of SEG_TOKENS capacity each
+    u32 nseg;         // segments in use
+    u32 edge_cur;     // which of the two edge arrays describes the current stream
+    ull drops;        // tokens removed by the merge in flight (summed by CTAs at exit)
+    u32 gather_exit;
+    u32 contig;       // 1: the current buffer is a contiguous stream whose edge records are stale
+    u64 reserved[2];
+};
+
+// ---- segmented stream ------------------------------------------------------------------------
+// The stream lives in fixed segments of SEG_TOKENS words: segment t owns words
+// [t*SEG_TOKENS, (t+1)*SEG_TOKENS) and holds `count` tokens at its start.  A merge compacts
+// every segment in place, so no cross-segment prefix sum (and no serial dependency between CTAs)
+// is needed; the stream order is (segment, offset).  Edge records let a CTA see the tokens next
+// to its segment without touching the neighbour's body while that body is being rewritten; they
+// are double-buffered by merge parity.
+#define SEG_TOKENS 4096
+#define SEG_SHIFT 12
+struct __align__(32) Edge {
+    u32 f[3];    // first three tokens (TOK_SENTINEL where the segment is shorter)
+    u32 l[2];    // last two tokens: l[1] = last, l[0] = the one before it
+    u32 count;
+    u32 pad[2];
 };
 
 // ---- small helpers -------------------------------------------------------------------------
@@ -127,6 +149,15 @@ __device__ __forceinline__ bool mbar_try_wait(u64 *bar, u32 parity) {
     return ok != 0;
 }
 __device__ __forceinline__ void mbar_wait(u64 *bar, u32 parity) { while (!mbar_try_wait(bar, parity)) {} }
+__device__ __forceinline__ void mbar_arrive(u64 *bar) {
+    u64 state;
+    asm volatile("mbarrier.arrive.release.cta.shared::cta.b64 %0, [%1];" : "=l"(state) : "r"(smem_addr(bar)) : "memory");
+    (void)state;
+}
+// barrier among a subset of the CTA's warps (id 1..15; id 0 is __syncthreads)
+__device__ __forceinline__ void named_bar_sync(u32 id, u32 nthreads) {
+    asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
+}
 
 // global -> shared bulk copy (SASS: UBLKCP); bytes, src and dst must be multiples of 16
 __device__ __forceinline__ void bulk_g2s(void *dst_smem, const void *src_gmem, u32 bytes, u64 *bar) {

@@ -40,6 +40,7 @@ static int encode_on(bpe_handle *h, const uint8_t *bytes, uint64_t n, const uint
     if (rc) return rc;
     if ((rc = mark_chunks(h, h->buf[0], offs, n_chunks, n))) return rc;
     if ((rc = reset_ctl_for_stream(h, n))) return rc;
+    if ((rc = build_edges(h, n))) return rc;
     h->loaded = true; h->bytes_only = true; h->table_valid = false;
     if ((rc = pull_ctl(h))) return rc;
 
@@ -61,6 +62,7 @@ static int encode_on(bpe_handle *h, const uint8_t *bytes, uint64_t n, const uint
         while (rounds_left > 0 && !h->h_ctl->done) {
             int k = 0;
             if ((rc = table_batch(h, V, std::min(h->opt_batch, rounds_left), &k))) { cudaFree(d_merges); return rc; }
+            maybe_repack(h);
             for (int i = 0; i < k; ++i) {
                 k_select_rank<<<(n_merges + 255) / 256, 256, 0, h->stream>>>(d_merges, n_merges, h->table, h->ctl);
                 k_select_rank_finish<<<1, 1, 0, h->stream>>>(d_merges, h->ctl);

@@ -36,49 +36,38 @@ __device__ __forceinline__ u32 desc_status(u64 d) { return (u32)(d >> 36) & 3u; 
 __device__ __forceinline__ u64 desc_value(u64 d) { return d & 0xfffffffffull; }
 
 // Decoupled look-back, executed by one full warp.  Returns the exclusive prefix of `agg`.
-// The stream order of the output is a serial dependency: a tile can only finish once some
-// predecessor knows its inclusive prefix, so the "known prefix" frontier advances by at most one
-// window per L2 round trip.  A 32-descriptor window caps the whole kernel near
-// 32 * 32 KB / 0.7 us = 1.5 TB/s on B200 (measured, profiles/r1_lookback.md), hence each lane polls
-// LB_Q descriptors per hop (window = 32*LB_Q tiles) and consumes the valid run in front of it.
-#define LB_Q 8
+// NOTE (profiles/r1_lookback.md): with ~450 tiles in flight the chain of inclusive prefixes is
+// the critical path of a contiguous compaction on B200 (the known-prefix frontier moves one
+// 32-tile window per L2 round trip, ~1.3-1.5 TB/s of stream traffic); the segmented stream of
+// k_merge_seg.cuh exists to avoid it.  This contiguous kernel remains for pairs (a,a) and packing.
 __device__ __forceinline__ u64 tile_lookback(u64 *desc, u32 tile, u32 epoch, u64 agg) {
     const u32 lane = lane_id();
-    const u32 ep = epoch & 0x3ffffffu;
     if (tile == 0) {
         if (lane == 0) st_volatile_u64(&desc[0], desc_pack(epoch, DESC_INC, agg));
         return 0;
     }
     if (lane == 0) st_volatile_u64(&desc[tile], desc_pack(epoch, DESC_AGG, agg));
     u64 excl = 0;
-    long long top = (long long)tile - 1;  // nearest predecessor not yet accounted for
+    long long top = (long long)tile - 1;
     for (;;) {
-        u64 d[LB_Q];
-#pragma unroll
-        for (int q = 0; q < LB_Q; ++q) {
-            const long long idx = top - (long long)lane - 32 * q;   // distance lane + 32q behind `top`
-            d[q] = (idx >= 0) ? ld_volatile_u64(&desc[idx]) : desc_pack(epoch, DESC_INC, 0);
+        const long long idx = top - (long long)lane;
+        u64 d;
+        bool ok;
+        do {
+            d = (idx >= 0) ? ld_volatile_u64(&desc[idx]) : desc_pack(epoch, DESC_INC, 0);
+            ok = (desc_epoch(d) == (epoch & 0x3ffffffu)) && (desc_status(d) != 0);
+        } while (!__all_sync(0xffffffffu, ok));
+        const u32 inc = __ballot_sync(0xffffffffu, desc_status(d) == DESC_INC);
+        u64 v = desc_value(d);
+        if (inc) {
+            const u32 first = __ffs(inc) - 1;  // nearest tile that already knows its inclusive prefix
+            if (lane > first) v = 0;
         }
-        u32 first_inv = 32 * LB_Q, first_inc = 32 * LB_Q;
-#pragma unroll
-        for (int q = 0; q < LB_Q; ++q) {
-            const bool valid = (desc_epoch(d[q]) == ep) && (desc_status(d[q]) != 0);
-            const u32 bi = __ballot_sync(0xffffffffu, !valid);
-            const u32 bc = __ballot_sync(0xffffffffu, valid && desc_status(d[q]) == DESC_INC);
-            if (bi && first_inv == 32 * LB_Q) first_inv = 32 * q + __ffs(bi) - 1;
-            if (bc && first_inc == 32 * LB_Q) first_inc = 32 * q + __ffs(bc) - 1;
-        }
-        const bool finish = first_inc < first_inv;                 // an inclusive prefix inside the valid run
-        const u32 lim = finish ? first_inc + 1 : first_inv;        // descriptors at distance < lim are consumed
-        u64 v = 0;
-#pragma unroll
-        for (int q = 0; q < LB_Q; ++q) if (lane + 32u * q < lim) v += desc_value(d[q]);
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
         excl += v;
-        if (finish) break;
-        top -= (long long)lim;
-        if (lim == 0) __nanosleep(64);   // the nearest predecessor has not published yet
+        if (inc) break;
+        top -= 32;
     }
     if (lane == 0) st_volatile_u64(&desc[tile], desc_pack(epoch, DESC_INC, excl + agg));
     return excl;

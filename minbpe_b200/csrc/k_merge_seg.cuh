@@ -1,0 +1,287 @@
+// k_merge_seg.cuh — the fused merge pass (base.py:25-41 + the statistics delta) for a != b on the
+// SEGMENTED stream: every 4096-word segment is compacted in place by one CTA, independently of
+// all other segments.  There is no prefix sum across segments, hence no serial dependency
+// between CTAs: the kernel is a pure stream pass.
+//
+//   read   4 * count bytes per segment        (one 1-D bulk async copy, TMA / UBLKCP)
+//   write  4 * new_count bytes, ONLY if the segment changed   (coalesced stores, same address range)
+//   + 32-byte edge records per segment (first 3 / last 2 tokens, count), double-buffered, so a
+//     CTA can see across its segment boundaries without reading a body that another CTA rewrites
+//
+// Warp roles: warp 8 lane 0 = producer (segment tickets, neighbour tokens, bulk copies through a
+// 3-stage mbarrier ring, fully decoupled from the consumers through full/empty barriers);
+// warps 0..7 = consumers (mark, warp-local scan, scatter to the staging tile, delta, copy-out).
+// The marking and delta rules are the ones documented in k_merge.cuh.
+#pragma once
+#include "common.cuh"
+#include "k_merge.cuh"
+#include "k_seg.cuh"
+
+#define MS_CWARPS 8
+#define MS_CTHREADS (MS_CWARPS * 32)
+#define MS_THREADS (MS_CTHREADS + 32)
+#define MS_WSPAN (SEG_TOKENS / MS_CWARPS)   // 512 tokens per consumer warp
+#define MS_STAGES 3
+#define MS_PAD 4                            // body starts at word 4 of a stage (16-byte aligned)
+#define MS_IN_WORDS (SEG_TOKENS + 8)
+#define MS_OUT_WORDS (SEG_TOKENS + SEG_TOKENS / 32 + 8)
+#define MS_SMEM_BYTES (MS_STAGES * MS_IN_WORDS * 4 + MS_OUT_WORDS * 4 + 512)
+#define MS_INVALID 0xffffffffu
+
+struct SegArgs {
+    Ctl *ctl;
+    u32 *buf0, *buf1;
+    Edge *e0, *e1;
+    ull *delta;   // [0,V) L, [V,2V) R, [2V] ZZ; NULL = plain merge
+    u32 V;
+    int force;
+};
+
+__global__ void __launch_bounds__(MS_THREADS, 3) k_merge_seg(SegArgs A) {
+    Ctl *ctl = A.ctl;
+    if (!A.force && (ctl->done || ctl->iter >= ctl->max_iter)) return;
+    if (ctl->a == ctl->b) return;  // pairs (a,a) take the pack + k_merge<true> path
+
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    u32 *s_in = reinterpret_cast<u32 *>(smem_raw);                    // [MS_STAGES][MS_IN_WORDS]
+    u32 *s_out = s_in + MS_STAGES * MS_IN_WORDS;                      // [MS_OUT_WORDS]
+    u64 *s_full = reinterpret_cast<u64 *>(s_out + MS_OUT_WORDS);      // [MS_STAGES]
+    u64 *s_empty = s_full + MS_STAGES;                                // [MS_STAGES]
+    u32 *s_seg = reinterpret_cast<u32 *>(s_empty + MS_STAGES);        // [MS_STAGES] segment id or MS_INVALID
+    u32 *s_cnt = s_seg + MS_STAGES;                                   // [MS_STAGES]
+    u32 *s_halo = s_cnt + MS_STAGES;                                  // [MS_STAGES][8]: P0 P1 N0 N1 N2
+    u32 *s_wtot = s_halo + MS_STAGES * 8;                             // [MS_CWARPS]
+    u32 *s_changed = s_wtot + MS_CWARPS;                              // [2]
+
+    const u32 tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const bool is_ctrl = (warp == MS_CWARPS);
+    const u64 n = ctl->n;
+    u32 *__restrict__ w = ctl->cur ? A.buf1 : A.buf0;                 // compacted in place
+    const Edge *__restrict__ e_cur = ctl->edge_cur ? A.e1 : A.e0;
+    Edge *__restrict__ e_next = ctl->edge_cur ? A.e0 : A.e1;
+    const u32 a = (u32)ctl->a, b = (u32)ctl->b, z = (u32)ctl->z;
+    const u32 nseg = ctl->nseg;
+
+    if (tid == 0) {
+        for (int s = 0; s < MS_STAGES; ++s) { mbar_init(&s_full[s], 1); mbar_init(&s_empty[s], MS_CWARPS); }
+        s_changed[0] = 0; s_changed[1] = 0;
+        fence_mbar_init();
+    }
+    __syncthreads();
+
+    if (is_ctrl) {
+        // ================= producer: one thread keeps the 3-stage ring full =================
+        if (lane == 0) {
+            for (u32 j = 0;; ++j) {
+                const u32 stage = j % MS_STAGES;
+                if (j >= MS_STAGES) mbar_wait(&s_empty[stage], ((j / MS_STAGES) - 1) & 1u);
+                u32 seg, cnt = 0;
+                for (;;) {  // next non-empty segment; empty ones only need their (empty) edge carried over
+                    seg = atomicAdd(&ctl->merge_ticket, 1u);
+                    if (seg >= nseg) break;
+                    cnt = e_cur[seg].count;
+                    if (cnt) break;
+                    Edge ed;
+                    edge_from_tokens(ed, nullptr, 0);
+                    e_next[seg] = ed;
+                }
+                if (seg >= nseg) { s_seg[stage] = MS_INVALID; mbar_arrive(&s_full[stage]); break; }
+                u32 N[3], P[2];
+                seg_neighbours(e_cur, seg, nseg, N, P);
+                u32 *h = s_halo + stage * 8;
+                h[0] = P[0]; h[1] = P[1]; h[2] = N[0]; h[3] = N[1]; h[4] = N[2];
+                s_seg[stage] = seg; s_cnt[stage] = cnt;
+                const u32 bytes = ((cnt + 3u) & ~3u) * 4u;
+                mbar_arrive_expect_tx(&s_full[stage], bytes);   // release: the stores above are visible to waiters
+                bulk_g2s(s_in + stage * MS_IN_WORDS + MS_PAD, w + (u64)seg * SEG_TOKENS, bytes, &s_full[stage]);
+            }
+        }
+    } else {
+        // ================= consumers =================
+        ull cta_drops = 0;  // meaningful in thread 0
+        for (u32 j = 0;; ++j) {
+            const u32 stage = j % MS_STAGES;
+            mbar_wait(&s_full[stage], (j / MS_STAGES) & 1u);
+            const u32 seg = s_seg[stage];
+            if (seg == MS_INVALID) break;
+            const u32 count = s_cnt[stage];
+            const u32 *s = s_in + stage * MS_IN_WORDS + MS_PAD;   // s[i] = token i of the segment
+            const u32 *h = s_halo + stage * 8;
+            // token i of the segment extended by its neighbours (i in [-2, count+3))
+            auto tok = [&](int i) -> u32 {
+                if (i < 0) return (i >= -2) ? h[-i - 1] : TOK_SENTINEL;
+                if ((u32)i >= count) return ((u32)i - count < 3u) ? h[2 + (u32)i - count] : TOK_SENTINEL;
+                return s[i];
+            };
+
+            u32 t[4][4], mn[4], keep[4], lpre[4], rowoff[4];
+            u32 wtot = 0, many = 0;
+            const u32 wbase = warp * MS_WSPAN;
+            if (wbase < count) {
+                u32 nxt[4], pbit[4];
+#pragma unroll
+                for (int r = 0; r < 4; ++r) {
+                    const u32 li = wbase + r * 128 + lane * 4;
+                    if (wbase + r * 128 < count) {
+                        const uint4 q = *reinterpret_cast<const uint4 *>(s + li);
+                        t[r][0] = q.x; t[r][1] = q.y; t[r][2] = q.z; t[r][3] = q.w;
+                        if (li + 4 > count) {  // lanes at / past the end see the following segment's tokens
+#pragma unroll
+                            for (int k = 0; k < 4; ++k) if (li + k >= count) t[r][k] = tok((int)(li + k));
+                        }
+                    } else {
+                        t[r][0] = t[r][1] = t[r][2] = t[r][3] = TOK_SENTINEL;
+                    }
+                }
+#pragma unroll
+                for (int r = 0; r < 4; ++r) {
+                    const u32 li = wbase + r * 128 + lane * 4;
+                    u32 v = __shfl_down_sync(0xffffffffu, t[r][0], 1);
+                    if (lane == 31) v = tok((int)(li + 4));
+                    nxt[r] = v;
+                }
+#pragma unroll
+                for (int r = 0; r < 4; ++r) {
+                    u32 m = 0;
+                    m |= (((t[r][0] ^ a) & TOK_MASK) == 0 && t[r][1] == b) ? 1u : 0u;
+                    m |= (((t[r][1] ^ a) & TOK_MASK) == 0 && t[r][2] == b) ? 2u : 0u;
+                    m |= (((t[r][2] ^ a) & TOK_MASK) == 0 && t[r][3] == b) ? 4u : 0u;
+                    m |= (((t[r][3] ^ a) & TOK_MASK) == 0 && nxt[r] == b) ? 8u : 0u;
+                    mn[r] = m;
+                }
+#pragma unroll
+                for (int r = 0; r < 4; ++r) {
+                    const u32 li = wbase + r * 128 + lane * 4;
+                    u32 pb = __shfl_up_sync(0xffffffffu, mn[r], 1) >> 3;
+                    if (lane == 0) {
+                        const u32 pv = tok((int)li - 1);
+                        pb = (((pv ^ a) & TOK_MASK) == 0 && t[r][0] == b) ? 1u : 0u;
+                    }
+                    pbit[r] = pb;
+                }
+                u32 dany = 0;
+#pragma unroll
+                for (int r = 0; r < 4; ++r) {
+                    const u32 li = wbase + r * 128 + lane * 4;
+                    const u32 d = ((mn[r] << 1) | pbit[r]) & 0xfu;
+                    const int rem = (int)count - (int)li;
+                    const u32 valid = rem >= 4 ? 0xfu : (rem <= 0 ? 0u : ((1u << rem) - 1u));
+                    mn[r] &= valid;             // a merge only starts at a token this segment owns
+                    keep[r] = ~d & valid;
+                    dany |= d | (valid ^ 0xfu);
+                    many |= mn[r];
+                }
+                if (!__any_sync(0xffffffffu, dany != 0)) {
+#pragma unroll
+                    for (int r = 0; r < 4; ++r) { lpre[r] = 4 * lane; rowoff[r] = 128 * r; }
+                    wtot = MS_WSPAN;
+                } else {
+                    u32 run = 0;
+#pragma unroll
+                    for (int r = 0; r < 4; ++r) {
+                        const u32 c = __popc(keep[r]);
+                        u32 incl = c;
+#pragma unroll
+                        for (int o = 1; o < 32; o <<= 1) { const u32 y = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= (u32)o) incl += y; }
+                        lpre[r] = incl - c;
+                        rowoff[r] = run;
+                        run += __shfl_sync(0xffffffffu, incl, 31);
+                    }
+                    wtot = run;
+                }
+            } else {
+#pragma unroll
+                for (int r = 0; r < 4; ++r) { mn[r] = 0; keep[r] = 0; lpre[r] = 0; rowoff[r] = 0; }
+            }
+            if (lane == 0) s_wtot[warp] = wtot;
+            named_bar_sync(1, MS_CTHREADS);  // (1) warp totals visible; staging tile free
+            if (tid == 0) s_changed[(j + 1) & 1] = 0;
+
+            u32 woff = 0, new_count = 0;
+#pragma unroll
+            for (u32 k = 0; k < MS_CWARPS; ++k) { const u32 v = s_wtot[k]; new_count += v; if (k < warp) woff += v; }
+            if (__any_sync(0xffffffffu, many != 0) && lane == 0) s_changed[j & 1] = 1;
+
+            if (wbase < count) {
+#pragma unroll
+                for (int r = 0; r < 4; ++r) {
+                    u32 dst = woff + rowoff[r] + lpre[r];
+#pragma unroll
+                    for (int k = 0; k < 4; ++k) {
+                        if ((keep[r] >> k) & 1u) {
+                            const u32 v = ((mn[r] >> k) & 1u) ? (z | (t[r][k] & TOK_FLAG)) : t[r][k];
+                            s_out[stage_idx(dst)] = v;
+                            ++dst;
+                        }
+                    }
+                }
+                if (A.delta && many) {
+#pragma unroll
+                    for (int r = 0; r < 4; ++r) {
+                        if (mn[r]) {
+#pragma unroll
+                            for (int k = 0; k < 4; ++k) {
+                                if ((mn[r] >> k) & 1u) {
+                                    const int i = (int)(wbase + r * 128 + lane * 4 + k);
+                                    const u32 tm1 = tok(i - 1), tm2 = tok(i - 2), tp2 = tok(i + 2), tp3 = tok(i + 3);
+                                    const bool m_m2 = (((tm2 ^ a) & TOK_MASK) == 0) && tm1 == b;   // merge at i-2
+                                    const bool m_p2 = (((tp2 ^ a) & TOK_MASK) == 0) && tp3 == b;   // merge at i+2
+                                    if (tm1 != TOK_SENTINEL && !(t[r][k] & TOK_FLAG) && !m_m2) atomicAdd(&A.delta[tm1 & TOK_MASK], 1ull);
+                                    if (!(tp2 & TOK_FLAG)) {   // also false for the sentinel (end of stream)
+                                        if (m_p2) atomicAdd(&A.delta[2 * (u64)A.V], 1ull);
+                                        else atomicAdd(&A.delta[(u64)A.V + tp2], 1ull);
+                                    }
+                                }
+                            }
+                        }
+                    }
+                }
+            }
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&s_empty[stage]);   // this warp no longer reads the input stage
+            named_bar_sync(1, MS_CTHREADS);  // (2) staging tile complete
+
+            const bool changed = (s_changed[j & 1] != 0) || (new_count != count);
+            if (changed) {
+                u32 *__restrict__ dstp = w + (u64)seg * SEG_TOKENS + tid;
+                const u32 *srcp = s_out + tid + (tid >> 5);
+#pragma unroll
+                for (int q = 0; q < SEG_TOKENS / MS_CTHREADS; ++q)
+                    if (q * MS_CTHREADS + tid < new_count) dstp[q * MS_CTHREADS] = srcp[q * (MS_CTHREADS + MS_CTHREADS / 32)];
+            }
+            if (tid == 0) {
+                Edge ed;
+                if (changed) {
+                    ed.count = new_count;
+#pragma unroll
+                    for (u32 k = 0; k < 3; ++k) ed.f[k] = (k < new_count) ? s_out[stage_idx(k)] : TOK_SENTINEL;
+                    ed.l[1] = new_count >= 1 ? s_out[stage_idx(new_count - 1)] : TOK_SENTINEL;
+                    ed.l[0] = new_count >= 2 ? s_out[stage_idx(new_count - 2)] : TOK_SENTINEL;
+                    ed.pad[0] = ed.pad[1] = 0;
+                } else {
+                    ed = e_cur[seg];
+                }
+                e_next[seg] = ed;
+                cta_drops += count - new_count;
+            }
+        }
+        named_bar_sync(1, MS_CTHREADS);
+        // ---- exit: the last CTA out publishes the new stream length and flips the edge arrays ----
+        if (tid == 0) {
+            if (cta_drops) atomicAdd(&ctl->drops, cta_drops);
+            __threadfence();
+            const u32 e = atomicAdd(&ctl->merge_exit, 1u);
+            if (e == gridDim.x - 1) {
+                __threadfence();
+                const ull dropped = *(volatile ull *)&ctl->drops;
+                ctl->sum_in += n; ctl->sum_out += n - dropped;
+                ctl->n = n - dropped;
+                ctl->drops = 0;
+                ctl->edge_cur ^= 1u;
+                ctl->iter += 1;
+                ctl->epoch += 1;
+                ctl->merge_ticket = 0; ctl->merge_exit = 0;
+            }
+        }
+    }
+}

@@ -3,39 +3,64 @@
 // incremental table update that follows a merge.
 #pragma once
 #include "common.cuh"
+#include "k_seg.cuh"
 
 // =============================================================================================
-// Full histogram of a BYTE stream (all ids < 256) into a dense 256x256 vector.
-// One pass, 4 tokens per thread per step (16-byte loads), warp-level de-duplication of equal
-// keys before the global reduction.  Used once per train() (iteration 0) — afterwards the table
-// is maintained incrementally by the merge kernel.  dense[p0*256+p1] += count.
+// Full histograms.  Both walk the segmented stream: one block per segment (grid-stride), four
+// tokens per thread per step (16-byte loads; segment bases are 16 KB aligned), equal keys inside
+// a warp are folded by __match_any_sync before the global reduction.  Stream position of token i
+// of segment t is t*SEG_TOKENS + i (monotone in stream order, used for first-occurrence order).
+// The pair (last token of t, first token of the next non-empty segment) belongs to segment t.
 // =============================================================================================
+struct SegTokens {
+    u32 t[5];       // four tokens starting at i0 and the token after them
+    u32 nvalid;     // how many of t[0..3] are real tokens of the segment
+};
+
+__device__ __forceinline__ SegTokens seg_load4(const u32 *__restrict__ seg, u32 count, u32 i0, const Edge *e, u32 t,
+                                               u32 nseg) {
+    SegTokens r;
+    if (i0 + 4 <= count) {
+        const uint4 q = *reinterpret_cast<const uint4 *>(seg + i0);
+        r.t[0] = q.x; r.t[1] = q.y; r.t[2] = q.z; r.t[3] = q.w;
+        r.nvalid = 4;
+    } else {
+#pragma unroll
+        for (int k = 0; k < 4; ++k) r.t[k] = (i0 + k < count) ? seg[i0 + k] : TOK_SENTINEL;
+        r.nvalid = count - i0;
+    }
+    r.t[4] = (i0 + 4 < count) ? seg[i0 + 4] : TOK_SENTINEL;
+    if (i0 + 4 >= count) {  // this thread owns the segment's last token: its right neighbour is in a later segment
+        const u32 nf = seg_next_first(e, t, nseg);
+        const u32 slot = count - i0;   // slot right after the last real token (1..4)
+#pragma unroll
+        for (u32 k = 1; k <= 4; ++k) if (slot == k) r.t[k] = nf;
+    }
+    return r;
+}
+
+// BYTE stream (all ids < 256) -> dense 256x256 vector, dense[p0*256+p1] += count.  Used once per
+// train() for iteration 0; afterwards the table is maintained incrementally by the merge pass.
 __global__ void __launch_bounds__(256) k_hist_dense(const u32 *__restrict__ buf0, const u32 *__restrict__ buf1,
-                                                    const Ctl *__restrict__ ctl, ull *__restrict__ dense,
-                                                    u32 *__restrict__ err) {
+                                                    const Ctl *__restrict__ ctl, const Edge *e0, const Edge *e1,
+                                                    ull *__restrict__ dense, u32 *__restrict__ err) {
     const u32 *__restrict__ w = ctl->cur ? buf1 : buf0;
-    const u64 n = ctl->n;
-    const u64 nvec = (n + 3) / 4;
-    for (u64 v = (u64)blockIdx.x * blockDim.x + threadIdx.x; v < nvec; v += (u64)gridDim.x * blockDim.x) {
-        const u64 p0 = v * 4;
-        u32 t[5];
-        if (p0 + 4 <= n) {
-            uint4 q = *reinterpret_cast<const uint4 *>(w + p0);
-            t[0] = q.x; t[1] = q.y; t[2] = q.z; t[3] = q.w;
-        } else {
+    const Edge *e = edges_cur(ctl, e0, e1);
+    const u32 nseg = ctl->nseg;
+    for (u32 t = blockIdx.x; t < nseg; t += gridDim.x) {
+        const u32 count = e[t].count;
+        const u32 *__restrict__ seg = w + (u64)t * SEG_TOKENS;
+        for (u32 i0 = threadIdx.x * 4; i0 < count; i0 += blockDim.x * 4) {
+            const SegTokens r = seg_load4(seg, count, i0, e, t, nseg);
 #pragma unroll
-            for (int k = 0; k < 4; ++k) t[k] = (p0 + k < n) ? w[p0 + k] : TOK_SENTINEL;
-        }
-        t[4] = (p0 + 4 < n) ? w[p0 + 4] : TOK_SENTINEL;
-#pragma unroll
-        for (int k = 0; k < 4; ++k) {
-            const u32 left = t[k] & TOK_MASK, right = t[k + 1];
-            const bool valid = (p0 + k < n) && !(right & TOK_FLAG);
-            if (valid && (left > 255u || right > 255u)) *err = 1;
-            const u32 key = valid ? ((left & 255u) << 8 | (right & 255u)) : 0xffffffffu;
-            // lanes with the same key elect one leader that adds the whole group
-            const u32 peers = __match_any_sync(__activemask(), key);
-            if (valid && (__ffs(peers) - 1) == (int)lane_id()) atomicAdd(&dense[key], (ull)__popc(peers));
+            for (int k = 0; k < 4; ++k) {
+                const u32 left = r.t[k] & TOK_MASK, right = r.t[k + 1];
+                const bool valid = ((u32)k < r.nvalid) && !(right & TOK_FLAG);
+                if (valid && (left > 255u || right > 255u)) *err = 1;
+                const u32 key = valid ? ((left & 255u) << 8 | (right & 255u)) : 0xffffffffu;
+                const u32 peers = __match_any_sync(__activemask(), key);
+                if (valid && (__ffs(peers) - 1) == (int)lane_id()) atomicAdd(&dense[key], (ull)__popc(peers));
+            }
         }
     }
 }
@@ -50,38 +75,30 @@ __global__ void k_dense_to_table(const ull *__restrict__ dense, Table t, Ctl *ct
     t.counts[slot] = c;
 }
 
-// =============================================================================================
-// Full histogram of an arbitrary stream into the hash table, with first-occurrence positions
-// (count += 1, first = min(first, p)).  This is get_stats() for the C ABI and the "rescan"
-// verification mode.  Same scan shape as k_hist_dense.
-// =============================================================================================
+// Arbitrary stream -> hash table with first-occurrence positions (count += 1, first = min).  This
+// is get_stats() (base.py:13-22) for the C ABI and the "rescan" verification mode.
 __global__ void __launch_bounds__(256) k_hist_hash(const u32 *__restrict__ buf0, const u32 *__restrict__ buf1,
-                                                   Ctl *ctl, Table t, int gated) {
+                                                   Ctl *ctl, const Edge *e0, const Edge *e1, Table tab, int gated) {
     if (gated && (ctl->done || ctl->iter >= ctl->max_iter)) return;
     const u32 *__restrict__ w = ctl->cur ? buf1 : buf0;
-    const u64 n = ctl->n;
-    const u64 nvec = (n + 3) / 4;
-    for (u64 v = (u64)blockIdx.x * blockDim.x + threadIdx.x; v < nvec; v += (u64)gridDim.x * blockDim.x) {
-        const u64 p0 = v * 4;
-        u32 tk[5];
-        if (p0 + 4 <= n) {
-            uint4 q = *reinterpret_cast<const uint4 *>(w + p0);
-            tk[0] = q.x; tk[1] = q.y; tk[2] = q.z; tk[3] = q.w;
-        } else {
+    const Edge *e = edges_cur(ctl, e0, e1);
+    const u32 nseg = ctl->nseg;
+    for (u32 t = blockIdx.x; t < nseg; t += gridDim.x) {
+        const u32 count = e[t].count;
+        const u32 *__restrict__ seg = w + (u64)t * SEG_TOKENS;
+        for (u32 i0 = threadIdx.x * 4; i0 < count; i0 += blockDim.x * 4) {
+            const SegTokens r = seg_load4(seg, count, i0, e, t, nseg);
 #pragma unroll
-            for (int k = 0; k < 4; ++k) tk[k] = (p0 + k < n) ? w[p0 + k] : TOK_SENTINEL;
-        }
-        tk[4] = (p0 + 4 < n) ? w[p0 + 4] : TOK_SENTINEL;
-#pragma unroll
-        for (int k = 0; k < 4; ++k) {
-            const bool valid = (p0 + k < n) && !(tk[k + 1] & TOK_FLAG);
-            const u64 key = valid ? pack_pair(tk[k] & TOK_MASK, tk[k + 1]) : KEY_EMPTY;
-            const u32 peers = __match_any_sync(__activemask(), key);
-            // the lowest lane of a group also holds the group's smallest position
-            if (valid && (__ffs(peers) - 1) == (int)lane_id()) {
-                const u64 slot = table_upsert(t, key, &ctl->table_used);
-                atomicAdd((ull *)&t.counts[slot], (ull)__popc(peers));
-                if (t.first) atomicMin((ull *)&t.first[slot], (ull)(p0 + k));
+            for (int k = 0; k < 4; ++k) {
+                const bool valid = ((u32)k < r.nvalid) && !(r.t[k + 1] & TOK_FLAG);
+                const u64 key = valid ? pack_pair(r.t[k] & TOK_MASK, r.t[k + 1]) : KEY_EMPTY;
+                const u32 peers = __match_any_sync(__activemask(), key);
+                // the lowest lane of a group also holds the group's smallest position
+                if (valid && (__ffs(peers) - 1) == (int)lane_id()) {
+                    const u64 slot = table_upsert(tab, key, &ctl->table_used);
+                    atomicAdd((ull *)&tab.counts[slot], (ull)__popc(peers));
+                    if (tab.first) atomicMin((ull *)&tab.first[slot], (ull)((u64)t * SEG_TOKENS + i0 + k));
+                }
             }
         }
     }
@@ -176,28 +193,29 @@ __global__ void __launch_bounds__(256) k_argmax(Table t, Ctl *ctl, Best *partial
 // hit (later tiles exit as soon as they see found_pos in front of them).  Expected cost is
 // n / (tied * count) tokens — a tiny prefix unless counts are ~1.
 // =============================================================================================
-#define FF_TILE 2048
 __global__ void __launch_bounds__(256) k_find_first(const u32 *__restrict__ buf0, const u32 *__restrict__ buf1,
-                                                    Table t, Ctl *ctl, int *log_pairs, long long *log_counts) {
+                                                    const Edge *e0, const Edge *e1, Table t, Ctl *ctl,
+                                                    int *log_pairs, long long *log_counts) {
     if (ctl->done || ctl->iter >= ctl->max_iter || ctl->n_tied <= 1) return;
     const u32 *w = ctl->cur ? buf1 : buf0;
-    const u64 n = ctl->n, best = ctl->best_count;
+    const Edge *e = edges_cur(ctl, e0, e1);
+    const u32 nseg = ctl->nseg;
+    const u64 best = ctl->best_count;
     __shared__ bool last;
     __shared__ u64 s_found;
-    for (u64 tile = blockIdx.x;; tile += gridDim.x) {
-        const u64 base = tile * FF_TILE;
+    for (u32 sg = blockIdx.x;; sg += gridDim.x) {   // segments in stream order
+        const u64 base = (u64)sg * SEG_TOKENS;
         if (threadIdx.x == 0) s_found = ld_volatile_u64(&ctl->found_pos);
         __syncthreads();
-        if (base >= n || s_found < base) break;  // block-uniform: a hit in front of this tile ends the scan
+        if (sg >= nseg || s_found < base) break;  // block-uniform: a hit in front of this segment ends the scan
+        const u32 count = e[sg].count;
+        const u32 *seg = w + base;
         u64 hit = POS_NONE;
-        for (u32 j = threadIdx.x; j < FF_TILE; j += blockDim.x) {
-            const u64 p = base + j;
-            if (p + 1 < n) {
-                const u32 right = w[p + 1];
-                if (!(right & TOK_FLAG)) {
-                    const u64 slot = table_find(t, pack_pair(w[p] & TOK_MASK, right));
-                    if (slot != POS_NONE && t.counts[slot] == best) { hit = p; break; }  // ascending j: first hit of this thread
-                }
+        for (u32 i = threadIdx.x; i < count; i += blockDim.x) {
+            const u32 right = (i + 1 < count) ? seg[i + 1] : seg_next_first(e, sg, nseg);
+            if (!(right & TOK_FLAG)) {
+                const u64 slot = table_find(t, pack_pair(seg[i] & TOK_MASK, right));
+                if (slot != POS_NONE && t.counts[slot] == best) { hit = base + i; break; }  // ascending i: this thread's first hit
             }
         }
         if (hit != POS_NONE) atomicMin((ull *)&ctl->found_pos, (ull)hit);
@@ -211,7 +229,11 @@ __global__ void __launch_bounds__(256) k_find_first(const u32 *__restrict__ buf0
         ctl->ff_exit = 0;
         const u64 p = ld_volatile_u64(&ctl->found_pos);
         if (p == POS_NONE) ctl->done = 1;  // cannot happen when the table matches the stream
-        else record_selection(ctl, (int)(w[p] & TOK_MASK), (int)w[p + 1], best, log_pairs, log_counts);
+        else {
+            const u32 sg = (u32)(p >> SEG_SHIFT), i = (u32)(p & (SEG_TOKENS - 1));
+            const u32 right = (i + 1 < e[sg].count) ? w[p + 1] : seg_next_first(e, sg, nseg);
+            record_selection(ctl, (int)(w[p] & TOK_MASK), (int)right, best, log_pairs, log_counts);
+        }
     }
 }
 
