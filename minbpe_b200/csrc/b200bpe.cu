@@ -492,13 +492,15 @@ extern "C" int bpe_merge(bpe_handle *h, int32_t a, int32_t b, int32_t idx, uint6
 
 // ------------------------------------------------------------------------------------------------
 // training loop (basic.py:31-45 / regex.py:49-66)
-static u64 auto_table_cap(bpe_handle *h, u64 n) {
+// The table starts small (the arg-max scans every slot each iteration) and doubles on demand:
+// k_apply_delta stops inserting at ctl->table_limit and raises ctl->overflow (handle_overflow).
+static u64 auto_table_cap(bpe_handle *h, u64 n_unbounded_inserts) {
     if (h->opt_table_log2) return 1ull << h->opt_table_log2;
-    u64 c = next_pow2(std::max<u64>(n / 8, 1));
-    c = std::max<u64>(c, 1ull << 16);
-    c = std::min<u64>(c, 1ull << 24);
+    u64 c = 1ull << 17;   // a byte stream has at most 65536 distinct pairs
+    while (c < 2 * n_unbounded_inserts + 2) c <<= 1;
     return c;
 }
+#define TABLE_MAX_LOAD 0.6
 
 static int ensure_delta(bpe_handle *h, u32 V) {
     if (h->delta && h->V >= V) return BPE_OK;
@@ -571,6 +573,24 @@ static void timed_merge(bpe_handle *h, ull *delta) {
     h->ev_used += 2;
 }
 
+// ctl->overflow was raised by k_apply_delta: some delta entries of the last performed merge are
+// still pending.  Double the table (dead pairs are dropped on the way), re-run the apply.
+static int handle_overflow(bpe_handle *h) {
+    int rc;
+    while (h->h_ctl->overflow) {
+        const u64 new_cap = (h->table.mask + 1) * 2;
+        if ((rc = rehash_table(h, new_cap))) return rc;
+        if ((rc = pull_ctl(h))) return rc;
+        h->h_ctl->overflow = 0;
+        h->h_ctl->table_limit = (u64)(TABLE_MAX_LOAD * (double)new_cap);
+        if ((rc = push_ctl(h))) return rc;
+        k_apply_delta<<<(h->V + 255) / 256, 256, 0, h->stream>>>(h->table, h->ctl, h->delta, h->V, 0, 0, 0, 1, 1);
+        h->tm.kernel_launches++;
+        if ((rc = pull_ctl(h))) return rc;
+    }
+    return BPE_OK;
+}
+
 // Between batches: when merges have emptied the segments below half full on average, pack the
 // stream into full segments again (fewer, fuller segments = less per-segment overhead).
 static void maybe_repack(bpe_handle *h) {
@@ -595,7 +615,7 @@ static void enqueue_iteration(bpe_handle *h) {
     if (h->opt_rescan) timed_merge(h, nullptr);
     else {
         timed_merge(h, h->delta);
-        k_apply_delta<<<(h->V + 255) / 256, 256, 0, h->stream>>>(h->table, h->ctl, h->delta, h->V, 0, 0, 0, 1);
+        k_apply_delta<<<(h->V + 255) / 256, 256, 0, h->stream>>>(h->table, h->ctl, h->delta, h->V, 0, 0, 0, 1, 0);
         h->tm.kernel_launches++;
     }
 }
@@ -628,11 +648,9 @@ extern "C" int bpe_train(bpe_handle *h, int32_t num_merges, int32_t first_idx, i
 
     // ---- initial statistics (the only full histogram of the run) ----
     CU(cudaEventRecord(ev0, h->stream));
-    u64 cap = auto_table_cap(h, h->h_ctl->n);
-    // the table must absorb one iteration's worst case (2V+1 new pairs) below 60 % load
-    while ((double)cap * 0.6 < 65536.0 + 4.0 * (2.0 * V + 1)) cap <<= 1;
-    if (h->opt_rescan) cap = std::max<u64>(cap, next_pow2(2 * h->h_ctl->n + 2));
-    const bool reuse = h->table_valid && h->table.keys && h->table.mask + 1 >= cap && !h->opt_rescan;
+    // only a non-byte stream (bpe_load_ids) or the rescan mode insert without the load check
+    u64 cap = auto_table_cap(h, (h->opt_rescan || !h->bytes_only) ? h->h_ctl->n : 0);
+    const bool reuse = h->table_valid && h->table.keys && !h->opt_rescan;  // continuing a previous bpe_train
     if (!reuse && (rc = build_table(h, cap))) return rc;
     h->table_valid = false;  // becomes true again when the loop ends cleanly
     u32 bad = 0;
@@ -641,6 +659,8 @@ extern "C" int bpe_train(bpe_handle *h, int32_t num_merges, int32_t first_idx, i
     if (bad) return fail(h, BPE_ERR_INTERNAL, "byte stream contains ids >= 256");
     h->h_ctl->iter = 0; h->h_ctl->done = 0; h->h_ctl->first_idx = (u32)first_idx; h->h_ctl->max_iter = (u32)num_merges;
     h->h_ctl->sum_in = 0; h->h_ctl->sum_out = 0;
+    h->h_ctl->overflow = 0;
+    h->h_ctl->table_limit = (u64)(TABLE_MAX_LOAD * (double)(h->table.mask + 1));
     if ((rc = push_ctl(h))) return rc;
     CU(cudaEventRecord(ev1, h->stream));
 
@@ -648,26 +668,13 @@ extern "C" int bpe_train(bpe_handle *h, int32_t num_merges, int32_t first_idx, i
     int done_iters = 0;
     bool exhausted = false;
     while (done_iters < num_merges && !exhausted) {
-        const u64 tcap = h->table.mask + 1;
-        const u64 used = h->h_ctl->table_used;
-        const double room = 0.6 * (double)tcap - (double)used;
-        int k = (int)std::min<double>((double)h->opt_batch, room / (2.0 * V + 1));
-        if (k < 1) {
-            // not even one worst-case iteration fits: drop dead pairs, grow if that is not enough
-            if ((rc = rehash_table(h, tcap))) return rc;
-            if ((rc = pull_ctl(h))) return rc;
-            if (0.6 * (double)tcap - (double)h->h_ctl->table_used < 4.0 * (2.0 * V + 1)) {
-                if ((rc = rehash_table(h, tcap * 2))) return rc;
-                if ((rc = pull_ctl(h))) return rc;
-            }
-            continue;
-        }
-        k = std::min(k, num_merges - done_iters);
+        const int k = std::min(h->opt_batch, num_merges - done_iters);
         maybe_repack(h);
         for (int i = 0; i < k; ++i) enqueue_iteration(h);
         CU(cudaGetLastError());
         if ((rc = pull_ctl(h))) return rc;
         drain_kernel_events(h);
+        if (h->h_ctl->overflow && (rc = handle_overflow(h))) return rc;
         done_iters = (int)h->h_ctl->iter;
         exhausted = h->h_ctl->done != 0;
     }

@@ -90,7 +90,9 @@ struct Ctl {
     ull drops;        // tokens removed by the merge in flight (summed by CTAs at exit)
     u32 gather_exit;
     u32 contig;       // 1: the current buffer is a contiguous stream whose edge records are stale
-    u64 reserved[2];
+    u64 table_limit;  // k_apply_delta stops inserting at this many occupied slots ...
+    u32 overflow;     // ... and raises this; the host grows the table and re-runs the apply
+    u32 pad1;
 };
 
 // ---- segmented stream ------------------------------------------------------------------------
@@ -148,7 +150,17 @@ __device__ __forceinline__ bool mbar_try_wait(u64 *bar, u32 parity) {
                  : "=r"(ok) : "r"(smem_addr(bar)), "r"(parity) : "memory");
     return ok != 0;
 }
-__device__ __forceinline__ void mbar_wait(u64 *bar, u32 parity) { while (!mbar_try_wait(bar, parity)) {} }
+// try_wait with a suspend-time hint: the thread sleeps in hardware until the phase completes (or
+// `ns` elapse) instead of burning issue slots in a polling loop; wake-up on completion is immediate
+__device__ __forceinline__ bool mbar_try_wait_hint(u64 *bar, u32 parity, u32 ns) {
+    u32 ok;
+    asm volatile("{\n\t.reg .pred P;\n\t"
+                 "mbarrier.try_wait.parity.shared::cta.b64 P, [%1], %2, %3;\n\t"
+                 "selp.b32 %0, 1, 0, P;\n\t}"
+                 : "=r"(ok) : "r"(smem_addr(bar)), "r"(parity), "r"(ns) : "memory");
+    return ok != 0;
+}
+__device__ __forceinline__ void mbar_wait(u64 *bar, u32 parity) { while (!mbar_try_wait_hint(bar, parity, 20000u)) {} }
 __device__ __forceinline__ void mbar_arrive(u64 *bar) {
     u64 state;
     asm volatile("mbarrier.arrive.release.cta.shared::cta.b64 %0, [%1];" : "=l"(state) : "r"(smem_addr(bar)) : "memory");

@@ -6,23 +6,6 @@
 // A6).  So encode is the training loop with arg-max replaced by "lowest rank whose pair count in
 // the table is non-zero": one k_select_rank + k_merge + k_apply_delta round per applicable rank.
 
-// how many iterations fit in the table before a host check; rehashes/grows when none fits
-static int table_batch(bpe_handle *h, u32 V, int want, int *k_out) {
-    for (;;) {
-        const u64 tcap = h->table.mask + 1;
-        const double room = 0.6 * (double)tcap - (double)h->h_ctl->table_used;
-        int k = (int)std::min<double>((double)want, room / (2.0 * V + 1));
-        if (k >= 1) { *k_out = k; return BPE_OK; }
-        int rc;
-        if ((rc = rehash_table(h, tcap))) return rc;
-        if ((rc = pull_ctl(h))) return rc;
-        if (0.6 * (double)tcap - (double)h->h_ctl->table_used < 4.0 * (2.0 * V + 1)) {
-            if ((rc = rehash_table(h, tcap * 2))) return rc;
-            if ((rc = pull_ctl(h))) return rc;
-        }
-    }
-}
-
 static int encode_on(bpe_handle *h, const uint8_t *bytes, uint64_t n, const uint64_t *offs, uint64_t n_chunks,
                      const int32_t *merges, int32_t n_merges, const uint8_t *byte_perm, int32_t *out_ids,
                      uint64_t out_cap, uint64_t *out_n) {
@@ -52,25 +35,33 @@ static int encode_on(bpe_handle *h, const uint8_t *bytes, uint64_t n, const uint
         cudaError_t e = cudaMemcpyAsync(d_merges, merges, (size_t)n_merges * 8, cudaMemcpyHostToDevice, h->stream);
         h->tm.h2d_bytes += (u64)n_merges * 8;
         if (e != cudaSuccess) { cudaFree(d_merges); return fail(h, BPE_ERR_CUDA, cudaGetErrorString(e)); }
-        u64 cap = auto_table_cap(h, n);
-        while ((double)cap * 0.6 < 65536.0 + 4.0 * (2.0 * V + 1)) cap <<= 1;
+        const u64 cap = auto_table_cap(h, 0);
         if ((rc = build_table(h, cap)) || (rc = pull_ctl(h))) { cudaFree(d_merges); return rc; }
+        h->h_ctl->overflow = 0;
+        h->h_ctl->table_limit = (u64)(TABLE_MAX_LOAD * (double)cap);
         h->h_ctl->iter = 0; h->h_ctl->done = 0; h->h_ctl->max_iter = 0xffffffffu; h->h_ctl->found_pos = POS_NONE;
         if ((rc = push_ctl(h))) { cudaFree(d_merges); return rc; }
         // at most one round per merge rank
         int rounds_left = n_merges;
         while (rounds_left > 0 && !h->h_ctl->done) {
-            int k = 0;
-            if ((rc = table_batch(h, V, std::min(h->opt_batch, rounds_left), &k))) { cudaFree(d_merges); return rc; }
+            const int k = std::min(h->opt_batch, rounds_left);
+            const int iters_before = (int)h->h_ctl->iter;
             maybe_repack(h);
             for (int i = 0; i < k; ++i) {
                 k_select_rank<<<(n_merges + 255) / 256, 256, 0, h->stream>>>(d_merges, n_merges, h->table, h->ctl);
                 k_select_rank_finish<<<1, 1, 0, h->stream>>>(d_merges, h->ctl);
                 launch_merge(h, h->delta, 0);
-                k_apply_delta<<<(h->V + 255) / 256, 256, 0, h->stream>>>(h->table, h->ctl, h->delta, h->V, 0, 0, 0, 1);
+                k_apply_delta<<<(h->V + 255) / 256, 256, 0, h->stream>>>(h->table, h->ctl, h->delta, h->V, 0, 0, 0, 1, 0);
                 h->tm.kernel_launches += 3;
             }
             if ((rc = pull_ctl(h))) { cudaFree(d_merges); return rc; }
+            if (h->h_ctl->overflow) {
+                // rounds after the overflowing one were skipped on the device: give them back
+                const int performed = (int)h->h_ctl->iter - iters_before;
+                if ((rc = handle_overflow(h))) { cudaFree(d_merges); return rc; }
+                rounds_left -= std::max(performed, 1);
+                continue;
+            }
             rounds_left -= k;
         }
         cudaFree(d_merges);

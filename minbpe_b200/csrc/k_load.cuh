@@ -54,7 +54,7 @@ __global__ void k_strip_flags(const u32 *__restrict__ src, int *__restrict__ dst
 // min(stats, key=merges.get)).  found = min rank via atomicMin; the finishing kernel turns it
 // into the next (a, b, z) or sets done.
 __global__ void __launch_bounds__(256) k_select_rank(const int *__restrict__ merges, int n_merges, Table t, Ctl *ctl) {
-    if (ctl->done) return;
+    if (ctl->done || ctl->overflow) return;
     const int r = blockIdx.x * blockDim.x + threadIdx.x;
     u64 hit = POS_NONE;
     if (r < n_merges) {
@@ -68,7 +68,7 @@ __global__ void __launch_bounds__(256) k_select_rank(const int *__restrict__ mer
 }
 
 __global__ void k_select_rank_finish(const int *__restrict__ merges, Ctl *ctl) {
-    if (ctl->done) return;
+    if (ctl->done || ctl->overflow) return;
     const u64 r = ctl->found_pos;
     if (r == POS_NONE) { ctl->done = 1; return; }
     ctl->a = merges[2 * r]; ctl->b = merges[2 * r + 1]; ctl->z = 256 + (int)r;

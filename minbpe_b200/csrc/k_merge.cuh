@@ -98,7 +98,7 @@ struct MergeArgs {
 template <bool SAME>
 __global__ void __launch_bounds__(MG_THREADS, SAME ? 2 : 3) k_merge(MergeArgs A) {
     Ctl *ctl = A.ctl;
-    if (!A.force && (ctl->done || ctl->iter >= ctl->max_iter)) return;
+    if (!A.force && (ctl->done || ctl->overflow || ctl->iter >= ctl->max_iter)) return;
     if ((ctl->a == ctl->b) != SAME) return;
 
     __shared__ u32 s_stage[MG_STAGE_WORDS];

@@ -24,8 +24,9 @@
 #define MS_STAGES 3
 #define MS_PAD 4                            // body starts at word 4 of a stage (16-byte aligned)
 #define MS_IN_WORDS (SEG_TOKENS + 8)
-#define MS_OUT_WORDS (SEG_TOKENS + SEG_TOKENS / 32 + 8)
-#define MS_SMEM_BYTES (MS_STAGES * MS_IN_WORDS * 4 + MS_OUT_WORDS * 4 + 512)
+#define MS_OUT_WORDS (SEG_TOKENS + 8)
+#define MS_DCACHE 1024                      // slots of the per-CTA delta cache (shared memory)
+#define MS_SMEM_BYTES (MS_STAGES * MS_IN_WORDS * 4 + MS_OUT_WORDS * 4 + MS_DCACHE * 8 + 512)
 #define MS_INVALID 0xffffffffu
 
 struct SegArgs {
@@ -39,7 +40,7 @@ struct SegArgs {
 
 __global__ void __launch_bounds__(MS_THREADS, 3) k_merge_seg(SegArgs A) {
     Ctl *ctl = A.ctl;
-    if (!A.force && (ctl->done || ctl->iter >= ctl->max_iter)) return;
+    if (!A.force && (ctl->done || ctl->overflow || ctl->iter >= ctl->max_iter)) return;
     if (ctl->a == ctl->b) return;  // pairs (a,a) take the pack + k_merge<true> path
 
     extern __shared__ __align__(128) unsigned char smem_raw[];
@@ -50,8 +51,9 @@ __global__ void __launch_bounds__(MS_THREADS, 3) k_merge_seg(SegArgs A) {
     u32 *s_seg = reinterpret_cast<u32 *>(s_empty + MS_STAGES);        // [MS_STAGES] segment id or MS_INVALID
     u32 *s_cnt = s_seg + MS_STAGES;                                   // [MS_STAGES]
     u32 *s_halo = s_cnt + MS_STAGES;                                  // [MS_STAGES][8]: P0 P1 N0 N1 N2
-    u32 *s_wtot = s_halo + MS_STAGES * 8;                             // [MS_CWARPS]
-    u32 *s_changed = s_wtot + MS_CWARPS;                              // [2]
+    u32 *s_wtot2 = s_halo + MS_STAGES * 8;                            // [2][MS_CWARPS], by tile parity
+    u32 *s_dkey = s_wtot2 + 2 * MS_CWARPS;                            // [MS_DCACHE] delta index or 0xffffffff
+    u32 *s_dcnt = s_dkey + MS_DCACHE;                                 // [MS_DCACHE]
 
     const u32 tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const bool is_ctrl = (warp == MS_CWARPS);
@@ -64,10 +66,28 @@ __global__ void __launch_bounds__(MS_THREADS, 3) k_merge_seg(SegArgs A) {
 
     if (tid == 0) {
         for (int s = 0; s < MS_STAGES; ++s) { mbar_init(&s_full[s], 1); mbar_init(&s_empty[s], MS_CWARPS); }
-        s_changed[0] = 0; s_changed[1] = 0;
         fence_mbar_init();
     }
+    for (u32 i = tid; i < MS_DCACHE; i += MS_THREADS) { s_dkey[i] = 0xffffffffu; s_dcnt[i] = 0; }
     __syncthreads();
+
+    // delta[idx] += 1 through a CTA-private shared-memory cache: the same few neighbour ids are hit
+    // by almost every merge of a dense iteration (global same-address atomics serialise in L2);
+    // the persistent CTA folds them here and flushes once at exit.
+    auto delta_add = [&](u32 idx) {
+        u32 slot = (idx * 2654435761u) >> (32 - 10);
+#pragma unroll 1
+        for (int probe = 0; probe < 4; ++probe) {
+            u32 k = reinterpret_cast<volatile u32 *>(s_dkey)[slot];
+            if (k == 0xffffffffu) {
+                const u32 old = atomicCAS(&s_dkey[slot], 0xffffffffu, idx);
+                k = (old == 0xffffffffu) ? idx : old;
+            }
+            if (k == idx) { atomicAdd(&s_dcnt[slot], 1u); return; }
+            slot = (slot + 1) & (MS_DCACHE - 1);
+        }
+        atomicAdd(&A.delta[idx], 1ull);   // cache neighbourhood full
+    };
 
     if (is_ctrl) {
         // ================= producer: one thread keeps the 3-stage ring full =================
@@ -107,6 +127,7 @@ __global__ void __launch_bounds__(MS_THREADS, 3) k_merge_seg(SegArgs A) {
             const u32 count = s_cnt[stage];
             const u32 *s = s_in + stage * MS_IN_WORDS + MS_PAD;   // s[i] = token i of the segment
             const u32 *h = s_halo + stage * 8;
+            u32 *s_wtot = s_wtot2 + (j & 1u) * MS_CWARPS;   // parity: an untouched segment skips barrier (2)
             // token i of the segment extended by its neighbours (i in [-2, count+3))
             auto tok = [&](int i) -> u32 {
                 if (i < 0) return (i >= -2) ? h[-i - 1] : TOK_SENTINEL;
@@ -116,6 +137,7 @@ __global__ void __launch_bounds__(MS_THREADS, 3) k_merge_seg(SegArgs A) {
 
             u32 t[4][4], mn[4], keep[4], lpre[4], rowoff[4];
             u32 wtot = 0, many = 0;
+            bool plain = true;   // warp-uniform: no token of this warp's span is removed or replaced
             const u32 wbase = warp * MS_WSPAN;
             if (wbase < count) {
                 u32 nxt[4], pbit[4];
@@ -159,7 +181,7 @@ __global__ void __launch_bounds__(MS_THREADS, 3) k_merge_seg(SegArgs A) {
                     }
                     pbit[r] = pb;
                 }
-                u32 dany = 0;
+                u32 rem_any = 0;   // some token of the lane is dropped or lies past the end of the segment
 #pragma unroll
                 for (int r = 0; r < 4; ++r) {
                     const u32 li = wbase + r * 128 + lane * 4;
@@ -168,24 +190,28 @@ __global__ void __launch_bounds__(MS_THREADS, 3) k_merge_seg(SegArgs A) {
                     const u32 valid = rem >= 4 ? 0xfu : (rem <= 0 ? 0u : ((1u << rem) - 1u));
                     mn[r] &= valid;             // a merge only starts at a token this segment owns
                     keep[r] = ~d & valid;
-                    dany |= d | (valid ^ 0xfu);
+                    rem_any |= keep[r] ^ 0xfu;
                     many |= mn[r];
                 }
-                if (!__any_sync(0xffffffffu, dany != 0)) {
+                many = __any_sync(0xffffffffu, many != 0) ? 1u : 0u;
+                if (!__any_sync(0xffffffffu, rem_any != 0)) {
 #pragma unroll
                     for (int r = 0; r < 4; ++r) { lpre[r] = 4 * lane; rowoff[r] = 128 * r; }
                     wtot = MS_WSPAN;
+                    plain = (many == 0);
                 } else {
+                    // removed tokens per lane (0..4) -> three ballots give the exclusive prefix
+                    plain = false;
                     u32 run = 0;
+                    const u32 lt = (1u << lane) - 1u;
 #pragma unroll
                     for (int r = 0; r < 4; ++r) {
-                        const u32 c = __popc(keep[r]);
-                        u32 incl = c;
-#pragma unroll
-                        for (int o = 1; o < 32; o <<= 1) { const u32 y = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= (u32)o) incl += y; }
-                        lpre[r] = incl - c;
+                        const u32 gone = 4u - __popc(keep[r]);
+                        const u32 b0 = __ballot_sync(0xffffffffu, gone & 1u), b1 = __ballot_sync(0xffffffffu, gone & 2u),
+                                  b2 = __ballot_sync(0xffffffffu, gone & 4u);
+                        lpre[r] = 4 * lane - (__popc(b0 & lt) + 2 * __popc(b1 & lt) + 4 * __popc(b2 & lt));
                         rowoff[r] = run;
-                        run += __shfl_sync(0xffffffffu, incl, 31);
+                        run += 128 - (__popc(b0) + 2 * __popc(b1) + 4 * __popc(b2));
                     }
                     wtot = run;
                 }
@@ -193,43 +219,71 @@ __global__ void __launch_bounds__(MS_THREADS, 3) k_merge_seg(SegArgs A) {
 #pragma unroll
                 for (int r = 0; r < 4; ++r) { mn[r] = 0; keep[r] = 0; lpre[r] = 0; rowoff[r] = 0; }
             }
-            if (lane == 0) s_wtot[warp] = wtot;
+            // bit 31 of the warp total = "this warp replaces a token" (a merge whose tail lies in
+            // the next warp / segment changes a token without removing one)
+            if (lane == 0) s_wtot[warp] = wtot | (many << 31);
             named_bar_sync(1, MS_CTHREADS);  // (1) warp totals visible; staging tile free
-            if (tid == 0) s_changed[(j + 1) & 1] = 0;
 
-            u32 woff = 0, new_count = 0;
+            u32 woff = 0, new_count = 0, chg = 0;
 #pragma unroll
-            for (u32 k = 0; k < MS_CWARPS; ++k) { const u32 v = s_wtot[k]; new_count += v; if (k < warp) woff += v; }
-            if (__any_sync(0xffffffffu, many != 0) && lane == 0) s_changed[j & 1] = 1;
+            for (u32 k = 0; k < MS_CWARPS; ++k) {
+                const u32 v = s_wtot[k];
+                chg |= v >> 31;
+                new_count += v & 0x7fffffffu;
+                if (k < warp) woff += v & 0x7fffffffu;
+            }
+            const bool changed = chg || (new_count != count);
+            if (!changed) {
+                // untouched segment: nothing to write, the edge record carries over
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&s_empty[stage]);
+                if (tid == 0) e_next[seg] = e_cur[seg];
+                continue;
+            }
 
             if (wbase < count) {
-#pragma unroll
-                for (int r = 0; r < 4; ++r) {
-                    u32 dst = woff + rowoff[r] + lpre[r];
-#pragma unroll
-                    for (int k = 0; k < 4; ++k) {
-                        if ((keep[r] >> k) & 1u) {
-                            const u32 v = ((mn[r] >> k) & 1u) ? (z | (t[r][k] & TOK_FLAG)) : t[r][k];
-                            s_out[stage_idx(dst)] = v;
-                            ++dst;
-                        }
-                    }
-                }
-                if (A.delta && many) {
+                if (plain) {   // whole warp keeps its 512 tokens unchanged: straight 16-byte copies
 #pragma unroll
                     for (int r = 0; r < 4; ++r) {
-                        if (mn[r]) {
+                        const u32 dst = woff + 128 * r + 4 * lane;
+                        if ((dst & 3u) == 0) {
+                            *reinterpret_cast<uint4 *>(s_out + dst) = make_uint4(t[r][0], t[r][1], t[r][2], t[r][3]);
+                        } else {
+                            s_out[dst] = t[r][0]; s_out[dst + 1] = t[r][1]; s_out[dst + 2] = t[r][2]; s_out[dst + 3] = t[r][3];
+                        }
+                    }
+                } else {
+#pragma unroll
+                    for (int r = 0; r < 4; ++r) {
+                        u32 dst = woff + rowoff[r] + lpre[r];
+                        if (keep[r] == 0xfu && mn[r] == 0) {
+                            s_out[dst] = t[r][0]; s_out[dst + 1] = t[r][1]; s_out[dst + 2] = t[r][2]; s_out[dst + 3] = t[r][3];
+                        } else {
 #pragma unroll
                             for (int k = 0; k < 4; ++k) {
-                                if ((mn[r] >> k) & 1u) {
-                                    const int i = (int)(wbase + r * 128 + lane * 4 + k);
-                                    const u32 tm1 = tok(i - 1), tm2 = tok(i - 2), tp2 = tok(i + 2), tp3 = tok(i + 3);
-                                    const bool m_m2 = (((tm2 ^ a) & TOK_MASK) == 0) && tm1 == b;   // merge at i-2
-                                    const bool m_p2 = (((tp2 ^ a) & TOK_MASK) == 0) && tp3 == b;   // merge at i+2
-                                    if (tm1 != TOK_SENTINEL && !(t[r][k] & TOK_FLAG) && !m_m2) atomicAdd(&A.delta[tm1 & TOK_MASK], 1ull);
-                                    if (!(tp2 & TOK_FLAG)) {   // also false for the sentinel (end of stream)
-                                        if (m_p2) atomicAdd(&A.delta[2 * (u64)A.V], 1ull);
-                                        else atomicAdd(&A.delta[(u64)A.V + tp2], 1ull);
+                                if ((keep[r] >> k) & 1u) {
+                                    s_out[dst] = ((mn[r] >> k) & 1u) ? (z | (t[r][k] & TOK_FLAG)) : t[r][k];
+                                    ++dst;
+                                }
+                            }
+                        }
+                    }
+                    if (A.delta && many) {
+#pragma unroll
+                        for (int r = 0; r < 4; ++r) {
+                            if (mn[r]) {
+#pragma unroll
+                                for (int k = 0; k < 4; ++k) {
+                                    if ((mn[r] >> k) & 1u) {
+                                        const int i = (int)(wbase + r * 128 + lane * 4 + k);
+                                        const u32 tm1 = tok(i - 1), tm2 = tok(i - 2), tp2 = tok(i + 2), tp3 = tok(i + 3);
+                                        const bool m_m2 = (((tm2 ^ a) & TOK_MASK) == 0) && tm1 == b;   // merge at i-2
+                                        const bool m_p2 = (((tp2 ^ a) & TOK_MASK) == 0) && tp3 == b;   // merge at i+2
+                                        if (tm1 != TOK_SENTINEL && !(t[r][k] & TOK_FLAG) && !m_m2) delta_add(tm1 & TOK_MASK);
+                                        if (!(tp2 & TOK_FLAG)) {   // also false for the sentinel (end of stream)
+                                            if (m_p2) delta_add(2u * A.V);
+                                            else delta_add(A.V + tp2);
+                                        }
                                     }
                                 }
                             }
@@ -241,30 +295,33 @@ __global__ void __launch_bounds__(MS_THREADS, 3) k_merge_seg(SegArgs A) {
             if (lane == 0) mbar_arrive(&s_empty[stage]);   // this warp no longer reads the input stage
             named_bar_sync(1, MS_CTHREADS);  // (2) staging tile complete
 
-            const bool changed = (s_changed[j & 1] != 0) || (new_count != count);
-            if (changed) {
-                u32 *__restrict__ dstp = w + (u64)seg * SEG_TOKENS + tid;
-                const u32 *srcp = s_out + tid + (tid >> 5);
+            {   // in place: the segment base is 16 KB aligned, so the copy-out is 16-byte vectors; up to
+                // three words past new_count are scribbled inside the segment's own capacity
+                uint4 *__restrict__ dstp = reinterpret_cast<uint4 *>(w + (u64)seg * SEG_TOKENS);
+                const uint4 *srcp = reinterpret_cast<const uint4 *>(s_out);
+                const u32 nvec = (new_count + 3u) >> 2;
 #pragma unroll
-                for (int q = 0; q < SEG_TOKENS / MS_CTHREADS; ++q)
-                    if (q * MS_CTHREADS + tid < new_count) dstp[q * MS_CTHREADS] = srcp[q * (MS_CTHREADS + MS_CTHREADS / 32)];
+                for (int q = 0; q < SEG_TOKENS / 4 / MS_CTHREADS; ++q) {
+                    const u32 v = q * MS_CTHREADS + tid;
+                    if (v < nvec) dstp[v] = srcp[v];
+                }
             }
             if (tid == 0) {
                 Edge ed;
-                if (changed) {
-                    ed.count = new_count;
+                ed.count = new_count;
 #pragma unroll
-                    for (u32 k = 0; k < 3; ++k) ed.f[k] = (k < new_count) ? s_out[stage_idx(k)] : TOK_SENTINEL;
-                    ed.l[1] = new_count >= 1 ? s_out[stage_idx(new_count - 1)] : TOK_SENTINEL;
-                    ed.l[0] = new_count >= 2 ? s_out[stage_idx(new_count - 2)] : TOK_SENTINEL;
-                    ed.pad[0] = ed.pad[1] = 0;
-                } else {
-                    ed = e_cur[seg];
-                }
+                for (u32 k = 0; k < 3; ++k) ed.f[k] = (k < new_count) ? s_out[k] : TOK_SENTINEL;
+                ed.l[1] = new_count >= 1 ? s_out[new_count - 1] : TOK_SENTINEL;
+                ed.l[0] = new_count >= 2 ? s_out[new_count - 2] : TOK_SENTINEL;
+                ed.pad[0] = ed.pad[1] = 0;
                 e_next[seg] = ed;
                 cta_drops += count - new_count;
             }
         }
+        named_bar_sync(1, MS_CTHREADS);
+        if (A.delta)
+            for (u32 i = tid; i < MS_DCACHE; i += MS_CTHREADS)
+                if (s_dkey[i] != 0xffffffffu && s_dcnt[i]) atomicAdd(&A.delta[s_dkey[i]], (ull)s_dcnt[i]);
         named_bar_sync(1, MS_CTHREADS);
         // ---- exit: the last CTA out publishes the new stream length and flips the edge arrays ----
         if (tid == 0) {

@@ -67,7 +67,7 @@ __global__ void __launch_bounds__(256) k_build_edges(const u32 *__restrict__ buf
 // gate shared by the packing kernels: forced by the host, or device-driven for a pair (a,a)
 __device__ __forceinline__ bool pack_wanted(const Ctl *ctl, int force) {
     if (force) return true;
-    return !ctl->done && ctl->iter < ctl->max_iter && ctl->a == ctl->b;
+    return !ctl->done && !ctl->overflow && ctl->iter < ctl->max_iter && ctl->a == ctl->b;
 }
 
 // exclusive prefix sum of the segment counts (one block; 1024 threads x contiguous slices)

@@ -79,7 +79,7 @@ __global__ void k_dense_to_table(const ull *__restrict__ dense, Table t, Ctl *ct
 // is get_stats() (base.py:13-22) for the C ABI and the "rescan" verification mode.
 __global__ void __launch_bounds__(256) k_hist_hash(const u32 *__restrict__ buf0, const u32 *__restrict__ buf1,
                                                    Ctl *ctl, const Edge *e0, const Edge *e1, Table tab, int gated) {
-    if (gated && (ctl->done || ctl->iter >= ctl->max_iter)) return;
+    if (gated && (ctl->done || ctl->overflow || ctl->iter >= ctl->max_iter)) return;
     const u32 *__restrict__ w = ctl->cur ? buf1 : buf0;
     const Edge *e = edges_cur(ctl, e0, e1);
     const u32 nseg = ctl->nseg;
@@ -137,7 +137,7 @@ __device__ __forceinline__ void record_selection(Ctl *ctl, int a, int b, u64 cou
 }
 
 __global__ void __launch_bounds__(256) k_argmax(Table t, Ctl *ctl, Best *partials, int *log_pairs, long long *log_counts) {
-    if (ctl->done || ctl->iter >= ctl->max_iter) return;
+    if (ctl->done || ctl->overflow || ctl->iter >= ctl->max_iter) return;
     const u64 cap = t.mask + 1;
     Best v; v.count = 0; v.slot = POS_NONE; v.tied = 0;
     // two 64-bit counts per 16-byte load
@@ -196,7 +196,7 @@ __global__ void __launch_bounds__(256) k_argmax(Table t, Ctl *ctl, Best *partial
 __global__ void __launch_bounds__(256) k_find_first(const u32 *__restrict__ buf0, const u32 *__restrict__ buf1,
                                                     const Edge *e0, const Edge *e1, Table t, Ctl *ctl,
                                                     int *log_pairs, long long *log_counts) {
-    if (ctl->done || ctl->iter >= ctl->max_iter || ctl->n_tied <= 1) return;
+    if (ctl->done || ctl->overflow || ctl->iter >= ctl->max_iter || ctl->n_tied <= 1) return;
     const u32 *w = ctl->cur ? buf1 : buf0;
     const Edge *e = edges_cur(ctl, e0, e1);
     const u32 nseg = ctl->nseg;
@@ -253,35 +253,48 @@ __device__ __forceinline__ void table_sub(const Table &t, u64 key, u64 skip_key,
     if (slot != POS_NONE) atomicAdd((ull *)&t.counts[slot], (ull)(0ull - d));
 }
 
+// Every non-zero delta entry creates exactly one new pair (it contains the new id z, so it cannot
+// be in the table yet).  A slot is reserved first; when the table is at its load limit the entry
+// is left untouched and ctl->overflow is raised: the host grows the table and re-runs this kernel
+// (`retry`), which applies exactly the entries that are still non-zero.
+__device__ __forceinline__ bool table_reserve(Ctl *ctl) {
+    const ull r = atomicAdd(&ctl->table_used, 1ull);
+    if (r < ctl->table_limit) return true;
+    atomicAdd(&ctl->table_used, (ull)(0ull - 1ull));
+    ctl->overflow = 1;
+    return false;
+}
+
 __global__ void __launch_bounds__(256) k_apply_delta(Table t, Ctl *ctl, ull *__restrict__ delta, u32 V,
-                                                     int a_arg, int b_arg, int z_arg, int use_ctl) {
+                                                     int a_arg, int b_arg, int z_arg, int use_ctl, int retry) {
     if (use_ctl && (ctl->done || ctl->iter > ctl->max_iter)) return;
+    if (use_ctl && ctl->overflow && !retry) return;   // an earlier iteration is waiting for the host
     const u32 a = use_ctl ? (u32)ctl->a : (u32)a_arg, b = use_ctl ? (u32)ctl->b : (u32)b_arg,
               z = use_ctl ? (u32)ctl->z : (u32)z_arg;
     const u64 kab = pack_pair(a, b);
     const u32 x = blockIdx.x * blockDim.x + threadIdx.x;
     if (x < V) {
         const ull l = delta[x];
-        if (l) {
+        if (l && table_reserve(ctl)) {
             delta[x] = 0;
             table_sub(t, pack_pair(x, a), kab, l);
-            const u64 s = table_upsert(t, pack_pair(x, z), &ctl->table_used);
+            const u64 s = table_upsert(t, pack_pair(x, z), nullptr);
             atomicAdd((ull *)&t.counts[s], l);
         }
         const ull r = delta[V + x];
-        if (r) {
+        if (r && table_reserve(ctl)) {
             delta[V + x] = 0;
             table_sub(t, pack_pair(b, x), kab, r);
-            const u64 s = table_upsert(t, pack_pair(z, x), &ctl->table_used);
+            const u64 s = table_upsert(t, pack_pair(z, x), nullptr);
             atomicAdd((ull *)&t.counts[s], r);
         }
     }
     if (x == 0) {
         const ull zz = delta[2 * (u64)V];
-        if (zz) {
+        if (zz && table_reserve(ctl)) {
             delta[2 * (u64)V] = 0;
             table_sub(t, pack_pair(b, a), kab, zz);
-            const u64 s = table_upsert(t, pack_pair(z, z), &ctl->table_used);
+            const u64 s = table_upsert(t, pack_pair(z, z), nullptr);
             atomicAdd((ull *)&t.counts[s], zz);
         }
         const u64 s = table_find(t, kab);

@@ -264,6 +264,24 @@ def test_rescan_mode_equals_incremental(eng, taylorswift):
     assert d1 == d2 == 64 and np.array_equal(p1, p2) and np.array_equal(c1, c2)
 
 
+def test_table_growth_path(eng, golden_train, taylorswift):
+    """Force a tiny pair table so that k_apply_delta hits its load limit repeatedly: the host grows
+    the table and re-runs the apply; merges and counts must not change."""
+    from minbpe_b200 import engine as E
+    g = golden_train["taylorswift_basic_512"]
+    eng.set_option(E.OPT_TABLE_LOG2, 13)
+    eng.set_option(E.OPT_BATCH, 7)
+    try:
+        eng.load_stream(taylorswift.encode("utf-8"), None)
+        pairs, counts, done = eng.train(256)
+        tm = eng.timing()
+    finally:
+        eng.set_option(E.OPT_TABLE_LOG2, 0)
+        eng.set_option(E.OPT_BATCH, 256)
+    assert done == 256 and pairs.tolist() == g["merges"] and counts.tolist() == g["counts"]
+    assert tm["table_slots"] > (1 << 13)  # it did grow
+
+
 def test_encode_vs_oracle_random(eng):
     rng = np.random.default_rng(5)
     text = "".join(rng.choice(list("abc de\n"), size=20000))
