@@ -137,7 +137,6 @@ extern "C" int bpe_create(int device, bpe_handle **out) {
     if ((e = cudaMalloc(&h->d_err, 4)) != cudaSuccess) return bail("cudaMalloc err", e);
     int occ = 1;
     int occ_same = 1;
-    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_merge<false>, MG_THREADS, 0);
     cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_same, k_merge<true>, MG_THREADS, 0);
     if (occ < 1) occ = 1;
     if (occ_same < 1) occ_same = 1;

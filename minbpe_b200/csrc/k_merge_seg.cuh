@@ -29,6 +29,50 @@
 #define MS_SMEM_BYTES (MS_STAGES * MS_IN_WORDS * 4 + MS_OUT_WORDS * 4 + MS_DCACHE * 8 + 512)
 #define MS_INVALID 0xffffffffu
 
+
+// token i of a segment extended by its neighbours: i in [-2, count+3); h = {P0,P1,N0,N1,N2}
+__device__ __noinline__ u32 seg_tok(const u32 *s, const u32 *h, u32 count, int i) {
+    if (i < 0) return (i >= -2) ? h[-i - 1] : TOK_SENTINEL;
+    if ((u32)i >= count) return ((u32)i - count < 3u) ? h[2 + (u32)i - count] : TOK_SENTINEL;
+    return s[i];
+}
+
+// delta[idx] += 1 through a CTA-private shared-memory cache: the same few neighbour ids are hit by
+// almost every merge of a dense iteration (global same-address atomics serialise in L2); the
+// persistent CTA folds them here and flushes once at exit.
+__device__ __noinline__ void delta_cache_add(u32 *s_dkey, u32 *s_dcnt, ull *delta, u32 idx) {
+    u32 slot = (idx * 2654435761u) >> (32 - 10);
+#pragma unroll 1
+    for (int probe = 0; probe < 4; ++probe) {
+        u32 k = reinterpret_cast<volatile u32 *>(s_dkey)[slot];
+        if (k == 0xffffffffu) {
+            const u32 old = atomicCAS(&s_dkey[slot], 0xffffffffu, idx);
+            k = (old == 0xffffffffu) ? idx : old;
+        }
+        if (k == idx) { atomicAdd(&s_dcnt[slot], 1u); return; }
+        slot = (slot + 1) & (MS_DCACHE - 1);
+    }
+    atomicAdd(&delta[idx], 1ull);   // cache neighbourhood full
+}
+
+// statistics delta of the merge that starts at token i of the segment (rules: k_merge.cuh)
+__device__ __noinline__ void delta_one(const u32 *s, const u32 *h, u32 count, int i, u32 a, u32 b, u32 V,
+                                       u32 *s_dkey, u32 *s_dcnt, ull *delta) {
+    const u32 t0 = s[i];
+    const u32 tm1 = seg_tok(s, h, count, i - 1), tm2 = seg_tok(s, h, count, i - 2);
+    const u32 tp2 = seg_tok(s, h, count, i + 2), tp3 = seg_tok(s, h, count, i + 3);
+    const bool m_m2 = (((tm2 ^ a) & TOK_MASK) == 0) && tm1 == b;   // a merge starts at i-2
+    const bool m_p2 = (((tp2 ^ a) & TOK_MASK) == 0) && tp3 == b;   // a merge starts at i+2
+    if (tm1 != TOK_SENTINEL && !(t0 & TOK_FLAG) && !m_m2) delta_cache_add(s_dkey, s_dcnt, delta, tm1 & TOK_MASK);
+    if (!(tp2 & TOK_FLAG))   // also false for the sentinel (end of stream)
+        delta_cache_add(s_dkey, s_dcnt, delta, m_p2 ? 2u * V : V + tp2);
+}
+
+// staging-tile swizzle at 16-byte granularity: word i lives in group (i>>2) ^ ((i>>5) & 7).  The
+// stride-4 scatter of the compaction (lane l writes word d+4l) and the 16-byte copy-out reads are
+// both bank-conflict free under it.
+__device__ __forceinline__ u32 swz(u32 i) { const u32 g = i >> 2; return ((g ^ ((g >> 3) & 7u)) << 2) | (i & 3u); }
+
 struct SegArgs {
     Ctl *ctl;
     u32 *buf0, *buf1;
@@ -71,24 +115,6 @@ __global__ void __launch_bounds__(MS_THREADS, 3) k_merge_seg(SegArgs A) {
     for (u32 i = tid; i < MS_DCACHE; i += MS_THREADS) { s_dkey[i] = 0xffffffffu; s_dcnt[i] = 0; }
     __syncthreads();
 
-    // delta[idx] += 1 through a CTA-private shared-memory cache: the same few neighbour ids are hit
-    // by almost every merge of a dense iteration (global same-address atomics serialise in L2);
-    // the persistent CTA folds them here and flushes once at exit.
-    auto delta_add = [&](u32 idx) {
-        u32 slot = (idx * 2654435761u) >> (32 - 10);
-#pragma unroll 1
-        for (int probe = 0; probe < 4; ++probe) {
-            u32 k = reinterpret_cast<volatile u32 *>(s_dkey)[slot];
-            if (k == 0xffffffffu) {
-                const u32 old = atomicCAS(&s_dkey[slot], 0xffffffffu, idx);
-                k = (old == 0xffffffffu) ? idx : old;
-            }
-            if (k == idx) { atomicAdd(&s_dcnt[slot], 1u); return; }
-            slot = (slot + 1) & (MS_DCACHE - 1);
-        }
-        atomicAdd(&A.delta[idx], 1ull);   // cache neighbourhood full
-    };
-
     if (is_ctrl) {
         // ================= producer: one thread keeps the 3-stage ring full =================
         if (lane == 0) {
@@ -129,11 +155,7 @@ __global__ void __launch_bounds__(MS_THREADS, 3) k_merge_seg(SegArgs A) {
             const u32 *h = s_halo + stage * 8;
             u32 *s_wtot = s_wtot2 + (j & 1u) * MS_CWARPS;   // parity: an untouched segment skips barrier (2)
             // token i of the segment extended by its neighbours (i in [-2, count+3))
-            auto tok = [&](int i) -> u32 {
-                if (i < 0) return (i >= -2) ? h[-i - 1] : TOK_SENTINEL;
-                if ((u32)i >= count) return ((u32)i - count < 3u) ? h[2 + (u32)i - count] : TOK_SENTINEL;
-                return s[i];
-            };
+            auto tok = [&](int i) -> u32 { return seg_tok(s, h, count, i); };
 
             u32 t[4][4], mn[4], keep[4], lpre[4], rowoff[4];
             u32 wtot = 0, many = 0;
@@ -247,9 +269,9 @@ __global__ void __launch_bounds__(MS_THREADS, 3) k_merge_seg(SegArgs A) {
                     for (int r = 0; r < 4; ++r) {
                         const u32 dst = woff + 128 * r + 4 * lane;
                         if ((dst & 3u) == 0) {
-                            *reinterpret_cast<uint4 *>(s_out + dst) = make_uint4(t[r][0], t[r][1], t[r][2], t[r][3]);
+                            *reinterpret_cast<uint4 *>(s_out + swz(dst)) = make_uint4(t[r][0], t[r][1], t[r][2], t[r][3]);
                         } else {
-                            s_out[dst] = t[r][0]; s_out[dst + 1] = t[r][1]; s_out[dst + 2] = t[r][2]; s_out[dst + 3] = t[r][3];
+                            s_out[swz(dst)] = t[r][0]; s_out[swz(dst + 1)] = t[r][1]; s_out[swz(dst + 2)] = t[r][2]; s_out[swz(dst + 3)] = t[r][3];
                         }
                     }
                 } else {
@@ -257,36 +279,25 @@ __global__ void __launch_bounds__(MS_THREADS, 3) k_merge_seg(SegArgs A) {
                     for (int r = 0; r < 4; ++r) {
                         u32 dst = woff + rowoff[r] + lpre[r];
                         if (keep[r] == 0xfu && mn[r] == 0) {
-                            s_out[dst] = t[r][0]; s_out[dst + 1] = t[r][1]; s_out[dst + 2] = t[r][2]; s_out[dst + 3] = t[r][3];
+                            s_out[swz(dst)] = t[r][0]; s_out[swz(dst + 1)] = t[r][1]; s_out[swz(dst + 2)] = t[r][2]; s_out[swz(dst + 3)] = t[r][3];
                         } else {
 #pragma unroll
                             for (int k = 0; k < 4; ++k) {
                                 if ((keep[r] >> k) & 1u) {
-                                    s_out[dst] = ((mn[r] >> k) & 1u) ? (z | (t[r][k] & TOK_FLAG)) : t[r][k];
+                                    s_out[swz(dst)] = ((mn[r] >> k) & 1u) ? (z | (t[r][k] & TOK_FLAG)) : t[r][k];
                                     ++dst;
                                 }
                             }
                         }
                     }
                     if (A.delta && many) {
-#pragma unroll
-                        for (int r = 0; r < 4; ++r) {
-                            if (mn[r]) {
-#pragma unroll
-                                for (int k = 0; k < 4; ++k) {
-                                    if ((mn[r] >> k) & 1u) {
-                                        const int i = (int)(wbase + r * 128 + lane * 4 + k);
-                                        const u32 tm1 = tok(i - 1), tm2 = tok(i - 2), tp2 = tok(i + 2), tp3 = tok(i + 3);
-                                        const bool m_m2 = (((tm2 ^ a) & TOK_MASK) == 0) && tm1 == b;   // merge at i-2
-                                        const bool m_p2 = (((tp2 ^ a) & TOK_MASK) == 0) && tp3 == b;   // merge at i+2
-                                        if (tm1 != TOK_SENTINEL && !(t[r][k] & TOK_FLAG) && !m_m2) delta_add(tm1 & TOK_MASK);
-                                        if (!(tp2 & TOK_FLAG)) {   // also false for the sentinel (end of stream)
-                                            if (m_p2) delta_add(2u * A.V);
-                                            else delta_add(A.V + tp2);
-                                        }
-                                    }
-                                }
-                            }
+                        u32 mall = mn[0] | (mn[1] << 4) | (mn[2] << 8) | (mn[3] << 12);
+#pragma unroll 1
+                        while (mall) {   // one pass per merge start of this lane
+                            const int bit = __ffs(mall) - 1;
+                            mall &= mall - 1;
+                            delta_one(s, h, count, (int)(wbase + (bit >> 2) * 128 + lane * 4 + (bit & 3)), a, b, A.V,
+                                      s_dkey, s_dcnt, A.delta);
                         }
                     }
                 }
@@ -303,16 +314,16 @@ __global__ void __launch_bounds__(MS_THREADS, 3) k_merge_seg(SegArgs A) {
 #pragma unroll
                 for (int q = 0; q < SEG_TOKENS / 4 / MS_CTHREADS; ++q) {
                     const u32 v = q * MS_CTHREADS + tid;
-                    if (v < nvec) dstp[v] = srcp[v];
+                    if (v < nvec) dstp[v] = srcp[v ^ ((v >> 3) & 7u)];
                 }
             }
             if (tid == 0) {
                 Edge ed;
                 ed.count = new_count;
 #pragma unroll
-                for (u32 k = 0; k < 3; ++k) ed.f[k] = (k < new_count) ? s_out[k] : TOK_SENTINEL;
-                ed.l[1] = new_count >= 1 ? s_out[new_count - 1] : TOK_SENTINEL;
-                ed.l[0] = new_count >= 2 ? s_out[new_count - 2] : TOK_SENTINEL;
+                for (u32 k = 0; k < 3; ++k) ed.f[k] = (k < new_count) ? s_out[swz(k)] : TOK_SENTINEL;
+                ed.l[1] = new_count >= 1 ? s_out[swz(new_count - 1)] : TOK_SENTINEL;
+                ed.l[0] = new_count >= 2 ? s_out[swz(new_count - 2)] : TOK_SENTINEL;
                 ed.pad[0] = ed.pad[1] = 0;
                 e_next[seg] = ed;
                 cta_drops += count - new_count;
