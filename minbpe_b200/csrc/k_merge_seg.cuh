@@ -59,8 +59,13 @@ __device__ __noinline__ void delta_cache_add(u32 *s_dkey, u32 *s_dcnt, ull *delt
 __device__ __noinline__ void delta_one(const u32 *s, const u32 *h, u32 count, int i, u32 a, u32 b, u32 V,
                                        u32 *s_dkey, u32 *s_dcnt, ull *delta) {
     const u32 t0 = s[i];
-    const u32 tm1 = seg_tok(s, h, count, i - 1), tm2 = seg_tok(s, h, count, i - 2);
-    const u32 tp2 = seg_tok(s, h, count, i + 2), tp3 = seg_tok(s, h, count, i + 3);
+    u32 tm1, tm2, tp2, tp3;
+    if (i >= 2 && (u32)i + 3 < count) {   // the usual case: all four neighbours inside the segment
+        tm1 = s[i - 1]; tm2 = s[i - 2]; tp2 = s[i + 2]; tp3 = s[i + 3];
+    } else {
+        tm1 = seg_tok(s, h, count, i - 1); tm2 = seg_tok(s, h, count, i - 2);
+        tp2 = seg_tok(s, h, count, i + 2); tp3 = seg_tok(s, h, count, i + 3);
+    }
     const bool m_m2 = (((tm2 ^ a) & TOK_MASK) == 0) && tm1 == b;   // a merge starts at i-2
     const bool m_p2 = (((tp2 ^ a) & TOK_MASK) == 0) && tp3 == b;   // a merge starts at i+2
     if (tm1 != TOK_SENTINEL && !(t0 & TOK_FLAG) && !m_m2) delta_cache_add(s_dkey, s_dcnt, delta, tm1 & TOK_MASK);
@@ -181,7 +186,7 @@ __global__ void __launch_bounds__(MS_THREADS, 3) k_merge_seg(SegArgs A) {
                 for (int r = 0; r < 4; ++r) {
                     const u32 li = wbase + r * 128 + lane * 4;
                     u32 v = __shfl_down_sync(0xffffffffu, t[r][0], 1);
-                    if (lane == 31) v = tok((int)(li + 4));
+                    if (lane == 31) v = (li + 4 < count) ? s[li + 4] : tok((int)(li + 4));
                     nxt[r] = v;
                 }
 #pragma unroll
@@ -198,7 +203,7 @@ __global__ void __launch_bounds__(MS_THREADS, 3) k_merge_seg(SegArgs A) {
                     const u32 li = wbase + r * 128 + lane * 4;
                     u32 pb = __shfl_up_sync(0xffffffffu, mn[r], 1) >> 3;
                     if (lane == 0) {
-                        const u32 pv = tok((int)li - 1);
+                        const u32 pv = (li >= 1) ? s[li - 1] : tok(-1);
                         pb = (((pv ^ a) & TOK_MASK) == 0 && t[r][0] == b) ? 1u : 0u;
                     }
                     pbit[r] = pb;
@@ -228,12 +233,17 @@ __global__ void __launch_bounds__(MS_THREADS, 3) k_merge_seg(SegArgs A) {
                     const u32 lt = (1u << lane) - 1u;
 #pragma unroll
                     for (int r = 0; r < 4; ++r) {
-                        const u32 gone = 4u - __popc(keep[r]);
-                        const u32 b0 = __ballot_sync(0xffffffffu, gone & 1u), b1 = __ballot_sync(0xffffffffu, gone & 2u),
-                                  b2 = __ballot_sync(0xffffffffu, gone & 4u);
-                        lpre[r] = 4 * lane - (__popc(b0 & lt) + 2 * __popc(b1 & lt) + 4 * __popc(b2 & lt));
                         rowoff[r] = run;
-                        run += 128 - (__popc(b0) + 2 * __popc(b1) + 4 * __popc(b2));
+                        if (!__any_sync(0xffffffffu, keep[r] != 0xfu)) {   // row keeps all of its 128 tokens
+                            lpre[r] = 4 * lane;
+                            run += 128;
+                        } else {
+                            const u32 gone = 4u - __popc(keep[r]);
+                            const u32 b0 = __ballot_sync(0xffffffffu, gone & 1u), b1 = __ballot_sync(0xffffffffu, gone & 2u),
+                                      b2 = __ballot_sync(0xffffffffu, gone & 4u);
+                            lpre[r] = 4 * lane - (__popc(b0 & lt) + 2 * __popc(b1 & lt) + 4 * __popc(b2 & lt));
+                            run += 128 - (__popc(b0) + 2 * __popc(b1) + 4 * __popc(b2));
+                        }
                     }
                     wtot = run;
                 }
@@ -279,7 +289,11 @@ __global__ void __launch_bounds__(MS_THREADS, 3) k_merge_seg(SegArgs A) {
                     for (int r = 0; r < 4; ++r) {
                         u32 dst = woff + rowoff[r] + lpre[r];
                         if (keep[r] == 0xfu && mn[r] == 0) {
-                            s_out[swz(dst)] = t[r][0]; s_out[swz(dst + 1)] = t[r][1]; s_out[swz(dst + 2)] = t[r][2]; s_out[swz(dst + 3)] = t[r][3];
+                            if ((dst & 3u) == 0) {
+                                *reinterpret_cast<uint4 *>(s_out + swz(dst)) = make_uint4(t[r][0], t[r][1], t[r][2], t[r][3]);
+                            } else {
+                                s_out[swz(dst)] = t[r][0]; s_out[swz(dst + 1)] = t[r][1]; s_out[swz(dst + 2)] = t[r][2]; s_out[swz(dst + 3)] = t[r][3];
+                            }
                         } else {
 #pragma unroll
                             for (int k = 0; k < 4; ++k) {
