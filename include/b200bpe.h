@@ -115,6 +115,36 @@ int bpe_encode(bpe_handle *h, const uint8_t *bytes, uint64_t n,
                const int32_t *merges, int32_t n_merges, const uint8_t *byte_perm,
                int32_t *out_ids, uint64_t out_cap, uint64_t *out_n);
 
+/* ---- step-wise training: the sharded (multi-GPU) loop ---------------------------------------- */
+/* One process per GPU, each holding a contiguous shard of the corpus (cut at chunk starts) and an
+ * identical copy of the global pair-count table.  Per merge the host (minbpe_b200/dist.py) issues
+ * two small collectives between these calls — MIN over one int64 (first-occurrence tie-break:
+ * lowest rank = earliest text wins, basic.py:35 semantics across shards) and SUM over the
+ * statistics delta vector — e.g. with torch.distributed / NCCL over NVLink.  *_dev parameters are
+ * device pointers on the handle's GPU.  All work is enqueued on the stream set by bpe_set_stream
+ * (the caller's stream, so its collectives are ordered with these kernels); nothing blocks the
+ * host except bpe_step_table / bpe_step_poll / bpe_step_result. */
+int bpe_set_stream(bpe_handle *h, void *cuda_stream /* cudaStream_t, NULL = the handle's own */);
+/* regex.py:51-54 at iteration 0 on this shard: dense_dev[p0*256+p1] = local count (65536 uint64). */
+int bpe_step_begin(bpe_handle *h, uint64_t *dense_dev);
+/* Build the table from the all-reduced vector; prepare num_merges iterations with new ids from
+ * first_idx.  poll_every = how many merges the host will enqueue between two bpe_step_poll calls. */
+int bpe_step_table(bpe_handle *h, const uint64_t *dense_dev, int32_t num_merges, int32_t first_idx, int32_t poll_every);
+/* regex.py:56 max(stats, key=stats.get): cand_dev[0] = rank << 58 | p0 << 29 | p1 for this rank's
+ * candidate (global max count; on a tie the pair that occurs first in this shard), INT64_MAX if
+ * this rank has none.  The host reduces cand_dev[0] with MIN across ranks. */
+int bpe_step_select(bpe_handle *h, int64_t *cand_dev, int32_t rank);
+/* regex.py:60 merge of the reduced winner in this shard; the statistics delta is added
+ * into delta_dev (uint64[bpe_step_delta_len], all zero on entry).  The host reduces it with SUM. */
+int bpe_step_merge(bpe_handle *h, const int64_t *cand_dev, uint64_t *delta_dev);
+/* Apply the summed delta to the table; zeroes delta_dev. */
+int bpe_step_apply(bpe_handle *h, uint64_t *delta_dev);
+int bpe_step_delta_len(bpe_handle *h, uint64_t *len);
+/* Host sync: merges completed, whether the corpus ran out of pairs (reference: ValueError). */
+int bpe_step_poll(bpe_handle *h, int32_t *iters_done, int32_t *exhausted);
+/* Pairs and (global) counts of the merges performed so far. */
+int bpe_step_result(bpe_handle *h, int32_t *out_pairs, int64_t *out_counts, int32_t cap, int32_t *n_done);
+
 /* ---- measurement --------------------------------------------------------------------------- */
 
 typedef struct {

@@ -24,7 +24,8 @@
 struct bpe_handle {
     int device = 0;
     int sms = 0;
-    cudaStream_t stream = nullptr;
+    cudaStream_t stream = nullptr;       // the stream every kernel of this handle runs on
+    cudaStream_t own_stream = nullptr;   // created by bpe_create; `stream` may point at a caller's stream instead
     std::string err;
 
     // token stream: two ping-pong buffers of cap_tokens words
@@ -48,6 +49,7 @@ struct bpe_handle {
     int argmax_grid = 0, merge_grid = 0, merge_grid_same = 0, merge_grid_seg = 0, ff_grid = 0;
 
     // options
+    int step_poll_every = 16;
     int opt_kernel_timing = 0, opt_rescan = 0, opt_batch = 256, opt_table_log2 = 0, opt_merge_impl = 1;
 
     bpe_timing tm = {};
@@ -130,7 +132,8 @@ extern "C" int bpe_create(int device, bpe_handle **out) {
         return fail(nullptr, BPE_ERR_CUDA, m);
     };
     if ((e = cudaSetDevice(device)) != cudaSuccess) return bail("cudaSetDevice", e);
-    if ((e = cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking)) != cudaSuccess) return bail("cudaStreamCreate", e);
+    if ((e = cudaStreamCreateWithFlags(&h->own_stream, cudaStreamNonBlocking)) != cudaSuccess) return bail("cudaStreamCreate", e);
+    h->stream = h->own_stream;
     if ((e = cudaMalloc(&h->ctl, sizeof(Ctl))) != cudaSuccess) return bail("cudaMalloc ctl", e);
     if ((e = cudaMallocHost(&h->h_ctl, sizeof(Ctl))) != cudaSuccess) return bail("cudaMallocHost", e);
     if ((e = cudaMalloc(&h->dense, 65536 * 8)) != cudaSuccess) return bail("cudaMalloc dense", e);
@@ -177,7 +180,7 @@ extern "C" int bpe_destroy(bpe_handle *h) {
     if (h->partials) cudaFree(h->partials);
     if (h->ctl) cudaFree(h->ctl);
     if (h->h_ctl) cudaFreeHost(h->h_ctl);
-    if (h->stream) cudaStreamDestroy(h->stream);
+    if (h->own_stream) cudaStreamDestroy(h->own_stream);
     delete h;
     return BPE_OK;
 }
@@ -609,7 +612,7 @@ static void enqueue_iteration(bpe_handle *h) {
         h->tm.kernel_launches++;
     }
     k_argmax<<<h->argmax_grid, 256, 0, h->stream>>>(h->table, h->ctl, h->partials, h->log_pairs, h->log_counts);
-    k_find_first<<<h->ff_grid, 256, 0, h->stream>>>(h->buf[0], h->buf[1], h->edge[0], h->edge[1], h->table, h->ctl, h->log_pairs, h->log_counts);
+    k_find_first<<<h->ff_grid, 256, 0, h->stream>>>(h->buf[0], h->buf[1], h->edge[0], h->edge[1], h->table, h->ctl, h->log_pairs, h->log_counts, 0);
     h->tm.kernel_launches += 2;
     if (h->opt_rescan) timed_merge(h, nullptr);
     else {
@@ -719,3 +722,4 @@ extern "C" int bpe_debug_table(bpe_handle *h, int32_t *pairs, int64_t *counts, u
 }
 
 #include "encode_host.inl"
+#include "step_host.inl"

@@ -195,7 +195,7 @@ __global__ void __launch_bounds__(256) k_argmax(Table t, Ctl *ctl, Best *partial
 // =============================================================================================
 __global__ void __launch_bounds__(256) k_find_first(const u32 *__restrict__ buf0, const u32 *__restrict__ buf1,
                                                     const Edge *e0, const Edge *e1, Table t, Ctl *ctl,
-                                                    int *log_pairs, long long *log_counts) {
+                                                    int *log_pairs, long long *log_counts, int sharded) {
     if (ctl->done || ctl->overflow || ctl->iter >= ctl->max_iter || ctl->n_tied <= 1) return;
     const u32 *w = ctl->cur ? buf1 : buf0;
     const Edge *e = edges_cur(ctl, e0, e1);
@@ -228,8 +228,10 @@ __global__ void __launch_bounds__(256) k_find_first(const u32 *__restrict__ buf0
         __threadfence();
         ctl->ff_exit = 0;
         const u64 p = ld_volatile_u64(&ctl->found_pos);
-        if (p == POS_NONE) ctl->done = 1;  // cannot happen when the table matches the stream
-        else {
+        if (p == POS_NONE) {
+            if (sharded) ctl->a = -1;   // none of the tied pairs occurs in this rank's shard
+            else ctl->done = 1;         // cannot happen when the table matches the stream
+        } else {
             const u32 sg = (u32)(p >> SEG_SHIFT), i = (u32)(p & (SEG_TOKENS - 1));
             const u32 right = (i + 1 < e[sg].count) ? w[p + 1] : seg_next_first(e, sg, nseg);
             record_selection(ctl, (int)(w[p] & TOK_MASK), (int)right, best, log_pairs, log_counts);
@@ -313,4 +315,24 @@ __global__ void k_rehash(Table src, Table dst, Ctl *ctl) {
             dst.counts[s] = c;
         }
     }
+}
+
+// =============================================================================================
+// Sharded training (one process per GPU, DESIGN.md "Multi-GPU"): every rank holds the same global
+// pair table, so the arg-max agrees everywhere; only a tie needs the ranks to talk, because the
+// reference's first-occurrence rule is "lowest rank (= earliest text) that sees a tied pair".
+// Each rank packs its local candidate into one int64, the host all-reduces it with MIN.
+//   word = rank << 58 | p0 << 29 | p1        (INT64_MAX: nothing to offer)
+// =============================================================================================
+#define CAND_NONE 0x7fffffffffffffffll
+__global__ void k_pack_candidate(const Ctl *ctl, long long *cand, int rank) {
+    if (ctl->done || ctl->overflow || ctl->iter >= ctl->max_iter || ctl->a < 0) { cand[0] = CAND_NONE; return; }
+    cand[0] = ((long long)rank << 58) | ((long long)ctl->a << 29) | (long long)ctl->b;
+}
+
+__global__ void k_commit_candidate(Ctl *ctl, const long long *cand, int *log_pairs, long long *log_counts) {
+    if (ctl->done || ctl->overflow || ctl->iter >= ctl->max_iter) return;
+    const long long w = cand[0];
+    if (w == CAND_NONE) { ctl->done = 1; return; }   // no rank has a pair left
+    record_selection(ctl, (int)((w >> 29) & 0x1fffffff), (int)(w & 0x1fffffff), ctl->best_count, log_pairs, log_counts);
 }

@@ -59,6 +59,15 @@ def load_library():
         "bpe_get_timing": ([vp, P(Timing)], ci),
         "bpe_set_option": ([vp, ci, i64], ci),
         "bpe_debug_table": ([vp, vp, vp, u64, P(u64)], ci),
+        "bpe_set_stream": ([vp, vp], ci),
+        "bpe_step_begin": ([vp, vp], ci),
+        "bpe_step_table": ([vp, vp, i32, i32, i32], ci),
+        "bpe_step_select": ([vp, vp, i32], ci),
+        "bpe_step_merge": ([vp, vp, vp], ci),
+        "bpe_step_apply": ([vp, vp], ci),
+        "bpe_step_delta_len": ([vp, P(u64)], ci),
+        "bpe_step_poll": ([vp, P(i32), P(i32)], ci),
+        "bpe_step_result": ([vp, vp, vp, i32, P(i32)], ci),
     }
     for name, (args, res) in sig.items():
         fn = getattr(L, name)  # AttributeError here = header/library mismatch
@@ -192,3 +201,40 @@ class Engine:
                 continue
             self._check(rc, "bpe_debug_table")
             return {(int(p[0]), int(p[1])): int(c) for p, c in zip(pairs[: n.value], counts[: n.value])}
+
+    # ---- step-wise training (sharded loop; device pointers, e.g. torch tensors' data_ptr()) ----
+    def set_stream(self, cuda_stream_ptr):
+        self._check(self._lib.bpe_set_stream(self._h, ctypes.c_void_p(cuda_stream_ptr)), "bpe_set_stream")
+
+    def step_begin(self, dense_ptr):
+        self._check(self._lib.bpe_step_begin(self._h, ctypes.c_void_p(dense_ptr)), "bpe_step_begin")
+
+    def step_table(self, dense_ptr, num_merges, first_idx=256, poll_every=16):
+        self._check(self._lib.bpe_step_table(self._h, ctypes.c_void_p(dense_ptr), int(num_merges), int(first_idx),
+                                             int(poll_every)), "bpe_step_table")
+
+    def step_delta_len(self):
+        n = ctypes.c_uint64()
+        self._check(self._lib.bpe_step_delta_len(self._h, ctypes.byref(n)), "bpe_step_delta_len")
+        return n.value
+
+    def step_select(self, cand_ptr, rank):
+        self._check(self._lib.bpe_step_select(self._h, ctypes.c_void_p(cand_ptr), int(rank)), "bpe_step_select")
+
+    def step_merge(self, cand_ptr, delta_ptr):
+        self._check(self._lib.bpe_step_merge(self._h, ctypes.c_void_p(cand_ptr), ctypes.c_void_p(delta_ptr)), "bpe_step_merge")
+
+    def step_apply(self, delta_ptr):
+        self._check(self._lib.bpe_step_apply(self._h, ctypes.c_void_p(delta_ptr)), "bpe_step_apply")
+
+    def step_poll(self):
+        it, ex = ctypes.c_int32(), ctypes.c_int32()
+        self._check(self._lib.bpe_step_poll(self._h, ctypes.byref(it), ctypes.byref(ex)), "bpe_step_poll")
+        return it.value, bool(ex.value)
+
+    def step_result(self, cap):
+        pairs = np.zeros((max(cap, 1), 2), dtype=np.int32)
+        counts = np.zeros(max(cap, 1), dtype=np.int64)
+        done = ctypes.c_int32()
+        self._check(self._lib.bpe_step_result(self._h, _ptr(pairs), _ptr(counts), int(cap), ctypes.byref(done)), "bpe_step_result")
+        return pairs[: done.value], counts[: done.value], done.value
