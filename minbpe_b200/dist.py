@@ -42,7 +42,14 @@ class GpuStepEngine:
     def __init__(self, engine, device):
         self.e = engine
         self.device = torch.device("cuda", device)
-        self.e.set_stream(torch.cuda.current_stream(self.device).cuda_stream)
+        # a dedicated torch stream shared by our kernels and (through torch's stream semantics) the
+        # NCCL collectives: the legacy default stream has handle 0, which bpe_set_stream reads as
+        # "use the handle's own stream" and which would leave kernels and collectives unordered
+        self.stream = torch.cuda.Stream(device=self.device)
+        self.e.set_stream(self.stream.cuda_stream)
+
+    def stream_ctx(self):
+        return torch.cuda.stream(self.stream)
 
     def new_i64(self, n):
         return torch.zeros(n, dtype=torch.int64, device=self.device)
@@ -84,30 +91,36 @@ class ShardedTrainer:
         if self.world > 1:
             dist.all_reduce(t, op=op, group=self.group)
 
+    def _ctx(self):
+        import contextlib
+        return self.eng.stream_ctx() if hasattr(self.eng, "stream_ctx") else contextlib.nullcontext()
+
     def prepare(self, num_merges, first_idx=256):
         """Iteration-0 statistics: local histograms, SUM across ranks, identical tables."""
         self.num_merges, self.first_idx = num_merges, first_idx
-        dense = self.eng.new_i64(65536)
-        self.eng.begin(dense)
-        self._allreduce(dense, dist.ReduceOp.SUM)
-        n_delta = self.eng.table(dense, num_merges, first_idx, self.poll_every)
-        self.cand = self.eng.new_i64(2)
-        self.delta = self.eng.new_i64(n_delta)
+        with self._ctx():
+            dense = self.eng.new_i64(65536)
+            self.eng.begin(dense)
+            self._allreduce(dense, dist.ReduceOp.SUM)
+            n_delta = self.eng.table(dense, num_merges, first_idx, self.poll_every)
+            self.cand = self.eng.new_i64(2)
+            self.delta = self.eng.new_i64(n_delta)
         self.done = 0
 
     def run(self, num_steps=None):
         """Enqueue merge iterations (all of them by default); returns (iterations done, exhausted)."""
         target = self.num_merges if num_steps is None else min(self.num_merges, self.done + num_steps)
         exhausted = False
-        while self.done < target and not exhausted:
-            k = min(self.poll_every, target - self.done)
-            for _ in range(k):
-                self.eng.select(self.cand, self.rank)
-                self._allreduce(self.cand[:1], dist.ReduceOp.MIN)
-                self.eng.merge(self.cand, self.delta)
-                self._allreduce(self.delta, dist.ReduceOp.SUM)
-                self.eng.apply(self.delta)
-            self.done, exhausted = self.eng.poll()
+        with self._ctx():
+            while self.done < target and not exhausted:
+                k = min(self.poll_every, target - self.done)
+                for _ in range(k):
+                    self.eng.select(self.cand, self.rank)
+                    self._allreduce(self.cand[:1], dist.ReduceOp.MIN)
+                    self.eng.merge(self.cand, self.delta)
+                    self._allreduce(self.delta, dist.ReduceOp.SUM)
+                    self.eng.apply(self.delta)
+                self.done, exhausted = self.eng.poll()
         return self.done, exhausted
 
     def result(self):
@@ -180,10 +193,10 @@ def bench_sharded(args, rank, world, local):
     tr.run(W)
     sync_all()
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    ev0.record()
+    ev0.record(step.stream)
     t0 = time.perf_counter()
     done, exhausted = tr.run(K)
-    ev1.record()
+    ev1.record(step.stream)
     sync_all()
     wall = time.perf_counter() - t0
     t_loop = torch.tensor([ev0.elapsed_time(ev1) / 1e3], device="cuda")   # kernels + collectives share torch's stream
