@@ -260,7 +260,7 @@ def run_ours(args):
         "wall_ms_per_step": wall / K * 1e3,
         "gpu_launches": int(tm["kernel_launches"]),
         "clocks": clocks,
-        "roofline": {"bound": "hbm", "kernel": "k_merge<false> (fused merge + compaction + stats delta)",
+        "roofline": {"bound": "hbm", "kernel": "k_merge_seg (fused merge + in-place segment compaction + stats delta)",
                      "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": None,
                      "peak_source": peak_src, "bytes_per_launch": (4.0 * n_in + 4.0 * n_out) / K, "ms_per_launch": k_ms,
                      "loop_frac_in_kernel": tm["merge_kernel_ms"] / tm["loop_ms"]},

@@ -6,6 +6,76 @@
 // A6).  So encode is the training loop with arg-max replaced by "lowest rank whose pair count in
 // the table is non-zero": one k_select_rank + k_merge + k_apply_delta round per applicable rank.
 
+// Chunk-parallel encode: one thread per chunk (one CTA per long chunk), ids written at the chunk's
+// byte offset, holes squeezed out per segment, then the ordinary pack + read-back.
+// *handled = 0 when some chunk exceeds ENC_LONG_MAX tokens (caller uses the stream rounds instead).
+static int encode_chunks_on(bpe_handle *h, const uint8_t *bytes, uint64_t n, const uint64_t *offs, uint64_t n_chunks,
+                            const int32_t *merges, int32_t n_merges, const uint8_t *byte_perm, int32_t *out_ids,
+                            uint64_t out_cap, uint64_t *out_n, int *handled) {
+    int rc;
+    *handled = 0;
+    const u64 one = 0;
+    if (!offs || n_chunks == 0) { offs = &one; n_chunks = 1; }
+    h->tm.h2d_bytes = 0; h->tm.d2h_bytes = 0; h->tm.kernel_launches = 0;
+    if ((rc = ensure_stream_capacity(h, n))) return rc;
+    unsigned char *d_bytes = nullptr, *d_perm = nullptr;
+    u64 *d_offs = nullptr, *d_keys = nullptr, *d_list = nullptr;
+    u32 *d_ranks = nullptr;
+    int *d_merges = nullptr;
+    ull *d_cnt = nullptr;
+    const u64 tcap = next_pow2(std::max<u64>(1024, 4ull * (u64)n_merges));
+    const u64 list_cap = n / ENC_LOCAL + 1;
+    auto cleanup = [&]() {
+        cudaFree(d_bytes); cudaFree(d_perm); cudaFree(d_offs); cudaFree(d_keys); cudaFree(d_list); cudaFree(d_ranks);
+        cudaFree(d_merges); cudaFree(d_cnt);
+    };
+#define ENC_CU(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) { cleanup(); return fail(h, BPE_ERR_CUDA, std::string(#call) + ": " + cudaGetErrorString(e_)); } } while (0)
+    ENC_CU(cudaMalloc(&d_bytes, n));
+    ENC_CU(cudaMalloc(&d_offs, n_chunks * 8));
+    ENC_CU(cudaMalloc(&d_keys, tcap * 8));
+    ENC_CU(cudaMalloc(&d_ranks, tcap * 4));
+    ENC_CU(cudaMalloc(&d_list, list_cap * 8));
+    ENC_CU(cudaMalloc(&d_cnt, 16));
+    ENC_CU(cudaMalloc(&d_merges, std::max<size_t>(8, (size_t)n_merges * 8)));
+    if (byte_perm) { ENC_CU(cudaMalloc(&d_perm, 256)); ENC_CU(cudaMemcpyAsync(d_perm, byte_perm, 256, cudaMemcpyHostToDevice, h->stream)); }
+    ENC_CU(cudaMemcpyAsync(d_bytes, bytes, n, cudaMemcpyHostToDevice, h->stream));
+    ENC_CU(cudaMemcpyAsync(d_offs, offs, n_chunks * 8, cudaMemcpyHostToDevice, h->stream));
+    if (n_merges) ENC_CU(cudaMemcpyAsync(d_merges, merges, (size_t)n_merges * 8, cudaMemcpyHostToDevice, h->stream));
+    h->tm.h2d_bytes = n + n_chunks * 8 + (u64)n_merges * 8;
+    ENC_CU(cudaMemsetAsync(d_keys, 0xff, tcap * 8, h->stream));
+    ENC_CU(cudaMemsetAsync(d_ranks, 0, tcap * 4, h->stream));
+    ENC_CU(cudaMemsetAsync(d_cnt, 0, 16, h->stream));
+    if (n_merges) k_rank_table_build<<<(n_merges + 255) / 256, 256, 0, h->stream>>>(d_merges, n_merges, d_keys, d_ranks, tcap - 1);
+    RankTable rt = {d_keys, d_ranks, tcap - 1};
+    k_encode_chunks<<<(unsigned)((n_chunks + 127) / 128), 128, 0, h->stream>>>(d_bytes, d_offs, n_chunks, n, rt, d_perm,
+                                                                             h->buf[0], d_list, d_cnt);
+    ull cnt[2] = {0, 0};
+    ENC_CU(cudaMemcpyAsync(cnt, d_cnt, 16, cudaMemcpyDeviceToHost, h->stream));
+    ENC_CU(cudaStreamSynchronize(h->stream));
+    h->tm.kernel_launches += 2;
+    if (cnt[1]) { cleanup(); return BPE_OK; }   // a chunk longer than ENC_LONG_MAX: not handled here
+    if (cnt[0]) {
+        ENC_CU(cudaFuncSetAttribute(k_encode_long, cudaFuncAttributeMaxDynamicSharedMemorySize, 2 * ENC_LONG_MAX * 4));
+        k_encode_long<<<(unsigned)std::min<u64>(cnt[0], (u64)h->sms * 2), 256, 2 * ENC_LONG_MAX * 4, h->stream>>>(
+            d_bytes, d_offs, n_chunks, n, d_list, cnt[0], rt, d_perm, h->buf[0]);
+        h->tm.kernel_launches += 1;
+    }
+    const u32 nseg = (u32)((n + SEG_TOKENS - 1) / SEG_TOKENS);
+    k_compact_holes<<<std::max(1u, std::min<u32>(nseg, (u32)h->sms * 8)), 256, 0, h->stream>>>(h->buf[0], n, h->edge[0]);
+    k_total_count<<<1, 1024, 0, h->stream>>>(h->ctl, h->edge[0], nseg);
+    h->tm.kernel_launches += 2;
+    ENC_CU(cudaGetLastError());
+    ENC_CU(cudaStreamSynchronize(h->stream));
+    cleanup();
+#undef ENC_CU
+    h->loaded = true; h->bytes_only = false; h->table_valid = false;
+    const u64 h2d = h->tm.h2d_bytes;
+    rc = bpe_read_stream(h, out_ids, out_cap, out_n);
+    h->tm.h2d_bytes = h2d;
+    *handled = 1;
+    return rc;
+}
+
 static int encode_on(bpe_handle *h, const uint8_t *bytes, uint64_t n, const uint64_t *offs, uint64_t n_chunks,
                      const int32_t *merges, int32_t n_merges, const uint8_t *byte_perm, int32_t *out_ids,
                      uint64_t out_cap, uint64_t *out_n) {
@@ -87,7 +157,13 @@ extern "C" int bpe_encode(bpe_handle *h, const uint8_t *bytes, uint64_t n, const
     int rc = bpe_create(h->device, &c);
     if (rc) return fail(h, rc, std::string("bpe_encode: ") + bpe_last_error(nullptr));
     c->opt_batch = h->opt_batch; c->opt_table_log2 = h->opt_table_log2;
-    rc = encode_on(c, bytes, n, chunk_offsets, n_chunks, merges, n_merges, byte_perm, out_ids, out_cap, out_n);
+    int handled = 0;
+    rc = BPE_OK;
+    if (n >= 1 && n_merges > 0 && (n_chunks >= 1 || n <= ENC_LONG_MAX))
+        rc = encode_chunks_on(c, bytes, n, chunk_offsets, n_chunks, merges, n_merges, byte_perm, out_ids, out_cap, out_n, &handled);
+    // one huge chunk (BasicTokenizer on a long text) or an oversized chunk: rank-ordered rounds on the stream kernels
+    if (!rc && !handled)
+        rc = encode_on(c, bytes, n, chunk_offsets, n_chunks, merges, n_merges, byte_perm, out_ids, out_cap, out_n);
     if (rc) h->err = c->err;
     h->tm.h2d_bytes = c->tm.h2d_bytes; h->tm.d2h_bytes = c->tm.d2h_bytes; h->tm.kernel_launches = c->tm.kernel_launches;
     bpe_destroy(c);

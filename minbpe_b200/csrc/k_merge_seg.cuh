@@ -9,7 +9,7 @@
 //     CTA can see across its segment boundaries without reading a body that another CTA rewrites
 //
 // Warp roles: warp 8 lane 0 = producer (segment tickets, neighbour tokens, bulk copies through a
-// 3-stage mbarrier ring, fully decoupled from the consumers through full/empty barriers);
+// 2-stage mbarrier ring, fully decoupled from the consumers through full/empty barriers);
 // warps 0..7 = consumers (mark, warp-local scan, scatter to the staging tile, delta, copy-out).
 // The marking and delta rules are the ones documented in k_merge.cuh.
 #pragma once
@@ -21,11 +21,21 @@
 #define MS_CTHREADS (MS_CWARPS * 32)
 #define MS_THREADS (MS_CTHREADS + 32)
 #define MS_WSPAN (SEG_TOKENS / MS_CWARPS)   // 512 tokens per consumer warp
-#define MS_STAGES 3
+// Tuned on B200 (profiles/r1_summary.md §5): 2 stages x 16 KB + 16 KB staging + 4 KB delta cache =
+// 53 KB -> 4 CTAs/SM at 56 registers (36 warps) beat 3 stages / 3 CTAs by 8 %.
+#ifndef MS_STAGES
+#define MS_STAGES 2
+#endif
+#ifndef MS_MINBLOCKS
+#define MS_MINBLOCKS 4
+#endif
+#ifndef MS_DCACHE_LOG2
+#define MS_DCACHE_LOG2 9
+#endif
 #define MS_PAD 4                            // body starts at word 4 of a stage (16-byte aligned)
 #define MS_IN_WORDS (SEG_TOKENS + 8)
 #define MS_OUT_WORDS (SEG_TOKENS + 8)
-#define MS_DCACHE 1024                      // slots of the per-CTA delta cache (shared memory)
+#define MS_DCACHE (1 << MS_DCACHE_LOG2)     // slots of the per-CTA delta cache (shared memory)
 #define MS_SMEM_BYTES (MS_STAGES * MS_IN_WORDS * 4 + MS_OUT_WORDS * 4 + MS_DCACHE * 8 + 512)
 #define MS_INVALID 0xffffffffu
 
@@ -41,7 +51,7 @@ __device__ __noinline__ u32 seg_tok(const u32 *s, const u32 *h, u32 count, int i
 // almost every merge of a dense iteration (global same-address atomics serialise in L2); the
 // persistent CTA folds them here and flushes once at exit.
 __device__ __noinline__ void delta_cache_add(u32 *s_dkey, u32 *s_dcnt, ull *delta, u32 idx) {
-    u32 slot = (idx * 2654435761u) >> (32 - 10);
+    u32 slot = (idx * 2654435761u) >> (32 - MS_DCACHE_LOG2);
 #pragma unroll 1
     for (int probe = 0; probe < 4; ++probe) {
         u32 k = reinterpret_cast<volatile u32 *>(s_dkey)[slot];
@@ -87,7 +97,7 @@ struct SegArgs {
     int force;
 };
 
-__global__ void __launch_bounds__(MS_THREADS, 3) k_merge_seg(SegArgs A) {
+__global__ void __launch_bounds__(MS_THREADS, MS_MINBLOCKS) k_merge_seg(SegArgs A) {
     Ctl *ctl = A.ctl;
     if (!A.force && (ctl->done || ctl->overflow || ctl->iter >= ctl->max_iter)) return;
     if (ctl->a == ctl->b) return;  // pairs (a,a) take the pack + k_merge<true> path

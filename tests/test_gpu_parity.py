@@ -368,3 +368,29 @@ def test_large_properties(eng):
         tied = np.flatnonzero(hist == top)
         first = min(int(np.flatnonzero(key == t)[0]) for t in tied)
         assert pairs[0].tolist() == [int(key[first]) // 256, int(key[first]) % 256]
+
+
+def test_encode_chunk_kernels_vs_oracle(eng):
+    """Chunk-parallel encode: thread-per-chunk kernel (short chunks), CTA-per-chunk kernel (chunks of
+    65..8192 tokens, incl. runs of one symbol = the a==a greedy rule), and the stream-round fallback
+    for a chunk beyond 8192 tokens — all against the oracle, with and without a byte permutation."""
+    from minbpe_b200.synth import generate
+    from minbpe_b200.tokenizer import split_text
+    text = generate(1337, 1 << 20).tobytes().decode("utf-8")
+    data, offs = split_text(GPT4, text)
+    eng.load_stream(data, offs)
+    merges, _, done = eng.train(200)
+    assert done == 200
+    # craft an input with long chunks: long words, long symbol runs, one whitespace run
+    extra = "x" * 70 + " " + "ab" * 500 + " " + "=" * 3000 + "\n" + "lyiltumdya" * 300 + " " + "z" * 8000 + " end"
+    for t in (text[:200000] + extra, extra, "a", "ab", "hello world"):
+        d2, o2 = split_text(GPT4, t)
+        want = oracle.c_encode(d2, o2, merges)
+        got = eng.encode(d2, o2, merges)
+        assert np.array_equal(got, want), (len(t), len(got), len(want))
+    perm = np.random.default_rng(3).permutation(256).astype(np.uint8)
+    d2, o2 = split_text(GPT4, text[:50000])
+    assert np.array_equal(eng.encode(d2, o2, merges, perm), oracle.c_encode(d2, o2, merges, perm))
+    # a single chunk longer than ENC_LONG_MAX -> stream-round path
+    long_one = ("lyiltumdya" * 1200).encode()
+    assert np.array_equal(eng.encode(long_one, None, merges), oracle.c_encode(long_one, None, merges))
