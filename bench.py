@@ -274,6 +274,37 @@ def run_ours(args):
     print(json.dumps(line), flush=True)
 
 
+def run_extras(args):
+    """--extras: side measurements recorded in profiles/ (not the contract line): cfg2 wall times and
+    chunk-parallel encode throughput (BASELINE configs[1] and configs[4] shapes)."""
+    import torch
+    from minbpe_b200 import BasicTokenizer, RegexTokenizer
+    from minbpe_b200 import engine as E
+    from minbpe_b200.presplit import chunk_offsets
+    from minbpe_b200.synth import generate
+    out = {}
+    text = open(os.path.join(ROOT, "tests", "golden", "taylorswift.txt"), encoding="utf-8").read()
+    for name, cls in (("basic", BasicTokenizer), ("regex", RegexTokenizer)):
+        tok = cls()
+        tok.train(text, 300)  # warm-up (context, allocations)
+        t0 = time.perf_counter(); tok.train(text, 512); torch.cuda.synchronize(); dt = time.perf_counter() - t0
+        t1 = time.perf_counter(); ids = tok.encode(text); torch.cuda.synchronize(); de = time.perf_counter() - t1
+        out[f"cfg2_{name}"] = {"train_wall_s": dt, "merges_per_s": 256 / dt, "loop_ms": tok.last_timing["loop_ms"],
+                               "encode_wall_s": de, "n_ids": len(ids)}
+    size = args.size_mib << 20
+    raw = generate(1339, size)
+    offs = chunk_offsets(GPT4, raw)
+    eng = E.Engine(0)
+    eng.load_stream(raw[: 64 << 20], offs[: int(np.searchsorted(offs, 64 << 20))])
+    merges, _, done = eng.train(2048)
+    torch.cuda.synchronize()
+    t0 = time.perf_counter(); ids = eng.encode(raw, offs, merges); torch.cuda.synchronize(); dt = time.perf_counter() - t0
+    tm = eng.timing()
+    out["encode"] = {"bytes": size, "merges": int(done), "chunks": int(offs.size), "ids": int(ids.size), "wall_s": dt,
+                     "GBps_e2e": size / dt / 1e9, "h2d_bytes": tm["h2d_bytes"], "d2h_bytes": tm["d2h_bytes"]}
+    print(json.dumps(out), flush=True)
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -284,10 +315,13 @@ def main():
     ap.add_argument("--seed", type=int, default=1337)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--merge-impl", type=int, default=None, help="development switch (BPE_OPT_MERGE_IMPL)")
+    ap.add_argument("--extras", action="store_true", help="side measurements (cfg2 wall time, encode throughput)")
     args = ap.parse_args()
     if args.warmup < 3 and args.impl == "ours":
         args.warmup = 3
-    if args.impl == "reference":
+    if args.extras:
+        run_extras(args)
+    elif args.impl == "reference":
         run_reference(args)
     else:
         run_ours(args)

@@ -530,7 +530,7 @@ static int build_table(bpe_handle *h, u64 cap) {
     if (h->bytes_only) {
         CU(cudaMemsetAsync(h->dense, 0, 65536 * 8, h->stream));
         CU(cudaMemsetAsync(h->d_err, 0, 4, h->stream));
-        k_hist_dense<<<h->sms * 8, 256, 0, h->stream>>>(h->buf[0], h->buf[1], h->ctl, h->edge[0], h->edge[1], h->dense, h->d_err);
+        k_hist_dense<<<h->sms * 3, 256, 0, h->stream>>>(h->buf[0], h->buf[1], h->ctl, h->edge[0], h->edge[1], h->dense, h->d_err);
         k_dense_to_table<<<65536 / 256, 256, 0, h->stream>>>(h->dense, h->table, h->ctl);
         h->tm.kernel_launches += 2;
     } else {

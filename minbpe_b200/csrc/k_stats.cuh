@@ -41,9 +41,16 @@ __device__ __forceinline__ SegTokens seg_load4(const u32 *__restrict__ seg, u32 
 
 // BYTE stream (all ids < 256) -> dense 256x256 vector, dense[p0*256+p1] += count.  Used once per
 // train() for iteration 0; afterwards the table is maintained incrementally by the merge pass.
+// Per-block open-addressing histogram in shared memory (text uses a few thousand of the 65,536
+// byte pairs), equal keys of a warp folded first with __match_any_sync, one flush per block.
+#define HD_SLOTS 4096
 __global__ void __launch_bounds__(256) k_hist_dense(const u32 *__restrict__ buf0, const u32 *__restrict__ buf1,
                                                     const Ctl *__restrict__ ctl, const Edge *e0, const Edge *e1,
                                                     ull *__restrict__ dense, u32 *__restrict__ err) {
+    __shared__ u32 s_key[HD_SLOTS];   // 16-bit pair or 0xffffffff
+    __shared__ u32 s_cnt[HD_SLOTS];
+    for (u32 i = threadIdx.x; i < HD_SLOTS; i += blockDim.x) { s_key[i] = 0xffffffffu; s_cnt[i] = 0; }
+    __syncthreads();
     const u32 *__restrict__ w = ctl->cur ? buf1 : buf0;
     const Edge *e = edges_cur(ctl, e0, e1);
     const u32 nseg = ctl->nseg;
@@ -59,10 +66,28 @@ __global__ void __launch_bounds__(256) k_hist_dense(const u32 *__restrict__ buf0
                 if (valid && (left > 255u || right > 255u)) *err = 1;
                 const u32 key = valid ? ((left & 255u) << 8 | (right & 255u)) : 0xffffffffu;
                 const u32 peers = __match_any_sync(__activemask(), key);
-                if (valid && (__ffs(peers) - 1) == (int)lane_id()) atomicAdd(&dense[key], (ull)__popc(peers));
+                if (valid && (__ffs(peers) - 1) == (int)lane_id()) {   // group leader adds the whole group
+                    const u32 add = __popc(peers);
+                    u32 slot = (key * 2654435761u) >> (32 - 12);
+                    bool placed = false;
+#pragma unroll 1
+                    for (int probe = 0; probe < 8 && !placed; ++probe) {
+                        u32 kk = reinterpret_cast<volatile u32 *>(s_key)[slot];
+                        if (kk == 0xffffffffu) {
+                            const u32 old = atomicCAS(&s_key[slot], 0xffffffffu, key);
+                            kk = (old == 0xffffffffu) ? key : old;
+                        }
+                        if (kk == key) { atomicAdd(&s_cnt[slot], add); placed = true; }
+                        slot = (slot + 1) & (HD_SLOTS - 1);
+                    }
+                    if (!placed) atomicAdd(&dense[key], (ull)add);
+                }
             }
         }
     }
+    __syncthreads();
+    for (u32 i = threadIdx.x; i < HD_SLOTS; i += blockDim.x)
+        if (s_key[i] != 0xffffffffu && s_cnt[i]) atomicAdd(&dense[s_key[i]], (ull)s_cnt[i]);
 }
 
 // dense 256x256 vector -> table entries (one thread per bin)

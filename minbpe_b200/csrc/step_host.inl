@@ -27,7 +27,7 @@ extern "C" int bpe_step_begin(bpe_handle *h, uint64_t *dense_dev) {
     CU(cudaSetDevice(h->device));
     CU(cudaMemsetAsync(dense_dev, 0, 65536 * 8, h->stream));
     CU(cudaMemsetAsync(h->d_err, 0, 4, h->stream));
-    k_hist_dense<<<h->sms * 8, 256, 0, h->stream>>>(h->buf[0], h->buf[1], h->ctl, h->edge[0], h->edge[1], (ull *)dense_dev, h->d_err);
+    k_hist_dense<<<h->sms * 3, 256, 0, h->stream>>>(h->buf[0], h->buf[1], h->ctl, h->edge[0], h->edge[1], (ull *)dense_dev, h->d_err);
     CU(cudaGetLastError());
     h->tm.kernel_launches = 1;
     return BPE_OK;
