@@ -151,6 +151,8 @@ __global__ void __launch_bounds__(MS_THREADS, MS_MINBLOCKS) k_merge_seg(SegArgs 
                 seg_neighbours(e_cur, seg, nseg, N, P);
                 u32 *h = s_halo + stage * 8;
                 h[0] = P[0]; h[1] = P[1]; h[2] = N[0]; h[3] = N[1]; h[4] = N[2];
+                s_in[stage * MS_IN_WORDS + MS_PAD - 1] = P[0];   // s[-1], s[-2] for the consumers' unconditional reads
+                s_in[stage * MS_IN_WORDS + MS_PAD - 2] = P[1];
                 s_seg[stage] = seg; s_cnt[stage] = cnt;
                 const u32 bytes = ((cnt + 3u) & ~3u) * 4u;
                 mbar_arrive_expect_tx(&s_full[stage], bytes);   // release: the stores above are visible to waiters
@@ -176,7 +178,30 @@ __global__ void __launch_bounds__(MS_THREADS, MS_MINBLOCKS) k_merge_seg(SegArgs 
             u32 wtot = 0, many = 0;
             bool plain = true;   // warp-uniform: no token of this warp's span is removed or replaced
             const u32 wbase = warp * MS_WSPAN;
-            if (wbase < count) {
+            // interior warp: its 512 tokens and the one after them all belong to this segment -> no
+            // bounds logic; neighbours come from shared memory (s[-1], s[-2] are filled by the producer)
+            const bool interior = (wbase + MS_WSPAN + 4 <= count);
+            u32 rem_any = 0;   // some token of the lane is dropped or lies past the end of the segment
+            if (interior) {
+#pragma unroll
+                for (int r = 0; r < 4; ++r) {
+                    const int li = (int)(wbase + r * 128 + lane * 4);
+                    const uint4 q = *reinterpret_cast<const uint4 *>(s + li);
+                    t[r][0] = q.x; t[r][1] = q.y; t[r][2] = q.z; t[r][3] = q.w;
+                    const u32 nx = s[li + 4], pv = s[li - 1];
+                    u32 m = 0;
+                    m |= (((t[r][0] ^ a) & TOK_MASK) == 0 && t[r][1] == b) ? 1u : 0u;
+                    m |= (((t[r][1] ^ a) & TOK_MASK) == 0 && t[r][2] == b) ? 2u : 0u;
+                    m |= (((t[r][2] ^ a) & TOK_MASK) == 0 && t[r][3] == b) ? 4u : 0u;
+                    m |= (((t[r][3] ^ a) & TOK_MASK) == 0 && nx == b) ? 8u : 0u;
+                    const u32 pm = (((pv ^ a) & TOK_MASK) == 0 && t[r][0] == b) ? 1u : 0u;
+                    const u32 d = ((m << 1) | pm) & 0xfu;
+                    mn[r] = m;
+                    keep[r] = d ^ 0xfu;
+                    rem_any |= d;
+                    many |= m;
+                }
+            } else if (wbase < count) {
                 u32 nxt[4], pbit[4];
 #pragma unroll
                 for (int r = 0; r < 4; ++r) {
@@ -218,7 +243,6 @@ __global__ void __launch_bounds__(MS_THREADS, MS_MINBLOCKS) k_merge_seg(SegArgs 
                     }
                     pbit[r] = pb;
                 }
-                u32 rem_any = 0;   // some token of the lane is dropped or lies past the end of the segment
 #pragma unroll
                 for (int r = 0; r < 4; ++r) {
                     const u32 li = wbase + r * 128 + lane * 4;
@@ -230,6 +254,12 @@ __global__ void __launch_bounds__(MS_THREADS, MS_MINBLOCKS) k_merge_seg(SegArgs 
                     rem_any |= keep[r] ^ 0xfu;
                     many |= mn[r];
                 }
+            } else {
+#pragma unroll
+                for (int r = 0; r < 4; ++r) { t[r][0] = t[r][1] = t[r][2] = t[r][3] = TOK_SENTINEL; mn[r] = 0; keep[r] = 0; }
+                rem_any = 1;
+            }
+            if (wbase < count) {
                 many = __any_sync(0xffffffffu, many != 0) ? 1u : 0u;
                 if (!__any_sync(0xffffffffu, rem_any != 0)) {
 #pragma unroll
