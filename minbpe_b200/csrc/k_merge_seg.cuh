@@ -36,7 +36,7 @@
 #define MS_IN_WORDS (SEG_TOKENS + 8)
 #define MS_OUT_WORDS (SEG_TOKENS + 8)
 #define MS_DCACHE (1 << MS_DCACHE_LOG2)     // slots of the per-CTA delta cache (shared memory)
-#define MS_SMEM_BYTES (MS_STAGES * MS_IN_WORDS * 4 + MS_OUT_WORDS * 4 + MS_DCACHE * 8 + 512)
+#define MS_SMEM_BYTES (MS_STAGES * MS_IN_WORDS * 4 + MS_OUT_WORDS * 4 + MS_DCACHE * 8 + 640)
 #define MS_INVALID 0xffffffffu
 
 
@@ -111,7 +111,8 @@ __global__ void __launch_bounds__(MS_THREADS, MS_MINBLOCKS) k_merge_seg(SegArgs 
     u32 *s_cnt = s_seg + MS_STAGES;                                   // [MS_STAGES]
     u32 *s_halo = s_cnt + MS_STAGES;                                  // [MS_STAGES][8]: P0 P1 N0 N1 N2
     u32 *s_wtot2 = s_halo + MS_STAGES * 8;                            // [2][MS_CWARPS], by tile parity
-    u32 *s_dkey = s_wtot2 + 2 * MS_CWARPS;                            // [MS_DCACHE] delta index or 0xffffffff
+    u32 *s_edge = s_wtot2 + 2 * MS_CWARPS;                            // [2][8] boundary tokens of the segment being written
+    u32 *s_dkey = s_edge + 16;                            // [MS_DCACHE] delta index or 0xffffffff
     u32 *s_dcnt = s_dkey + MS_DCACHE;                                 // [MS_DCACHE]
 
     const u32 tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -162,6 +163,21 @@ __global__ void __launch_bounds__(MS_THREADS, MS_MINBLOCKS) k_merge_seg(SegArgs 
     } else {
         // ================= consumers =================
         ull cta_drops = 0;  // meaningful in thread 0
+        // thread 0: the edge record of the previous changed segment is assembled one barrier later,
+        // when every warp has finished its copy-out and deposited the boundary tokens in s_edge
+        bool pending = false; u32 pend_seg = 0, pend_count = 0, pend_par = 0;
+        auto flush_edge = [&]() {
+            if (!pending) return;
+            const u32 *se = s_edge + pend_par * 8;
+            Edge ed;
+            ed.count = pend_count;
+            for (u32 k = 0; k < 3; ++k) ed.f[k] = (k < pend_count) ? se[k] : TOK_SENTINEL;
+            ed.l[0] = pend_count >= 2 ? se[3] : TOK_SENTINEL;
+            ed.l[1] = pend_count >= 1 ? se[4] : TOK_SENTINEL;
+            ed.pad[0] = ed.pad[1] = 0;
+            e_next[pend_seg] = ed;
+            pending = false;
+        };
         for (u32 j = 0;; ++j) {
             const u32 stage = j % MS_STAGES;
             mbar_wait(&s_full[stage], (j / MS_STAGES) & 1u);
@@ -294,7 +310,8 @@ __global__ void __launch_bounds__(MS_THREADS, MS_MINBLOCKS) k_merge_seg(SegArgs 
             // bit 31 of the warp total = "this warp replaces a token" (a merge whose tail lies in
             // the next warp / segment changes a token without removing one)
             if (lane == 0) s_wtot[warp] = wtot | (many << 31);
-            named_bar_sync(1, MS_CTHREADS);  // (1) warp totals visible; staging tile free
+            named_bar_sync(1, MS_CTHREADS);  // (1) warp totals visible; staging tile free; previous copy-out done
+            if (tid == 0) flush_edge();
 
             u32 woff = 0, new_count = 0, chg = 0;
 #pragma unroll
@@ -356,34 +373,36 @@ __global__ void __launch_bounds__(MS_THREADS, MS_MINBLOCKS) k_merge_seg(SegArgs 
                     }
                 }
             }
-            __syncwarp();
+            __syncwarp();   // the warp's own range [woff, woff + wtot) of the staging tile is complete
             if (lane == 0) mbar_arrive(&s_empty[stage]);   // this warp no longer reads the input stage
-            named_bar_sync(1, MS_CTHREADS);  // (2) staging tile complete
 
-            {   // in place: the segment base is 16 KB aligned, so the copy-out is 16-byte vectors; up to
-                // three words past new_count are scribbled inside the segment's own capacity
-                uint4 *__restrict__ dstp = reinterpret_cast<uint4 *>(w + (u64)seg * SEG_TOKENS);
-                const uint4 *srcp = reinterpret_cast<const uint4 *>(s_out);
-                const u32 nvec = (new_count + 3u) >> 2;
-#pragma unroll
-                for (int q = 0; q < SEG_TOKENS / 4 / MS_CTHREADS; ++q) {
-                    const u32 v = q * MS_CTHREADS + tid;
-                    if (v < nvec) dstp[v] = srcp[v ^ ((v >> 3) & 7u)];
+            // ---- copy-out, warp by warp (no second block barrier): every warp streams its own range of
+            // the compacted segment; whole 16-byte groups go as vectors (segment base is 16 KB aligned),
+            // the ragged ends shared with the neighbouring warps' ranges as single words ----
+            if (wtot) {
+                u32 *__restrict__ segp = w + (u64)seg * SEG_TOKENS;
+                const u32 lo = woff, hi = woff + wtot;
+                const u32 v0 = (lo + 3u) >> 2, v1 = hi >> 2;   // groups fully inside [lo, hi)
+                if (v1 > v0) {
+                    for (u32 v = v0 + lane; v < v1; v += 32)
+                        reinterpret_cast<uint4 *>(segp)[v] = reinterpret_cast<const uint4 *>(s_out)[v ^ ((v >> 3) & 7u)];
+                    if (lane < 3) { const u32 i = lo + lane; if (i < 4 * v0) segp[i] = s_out[swz(i)]; }            // head
+                    else if (lane < 6) { const u32 i = 4 * v1 + (lane - 3); if (i < hi) segp[i] = s_out[swz(i)]; }  // tail
+                } else {
+                    for (u32 i = lo + lane; i < hi; i += 32) segp[i] = s_out[swz(i)];
                 }
+                // tokens of the new edge record that fall into this warp's range
+                u32 *se = s_edge + (j & 1u) * 8;
+                if (lane < 3) { const u32 i = lane; if (i >= lo && i < hi) se[lane] = s_out[swz(i)]; }
+                else if (lane < 5) { const u32 back = 5 - lane; if (new_count >= back) { const u32 i = new_count - back; if (i >= lo && i < hi) se[lane] = s_out[swz(i)]; } }
             }
             if (tid == 0) {
-                Edge ed;
-                ed.count = new_count;
-#pragma unroll
-                for (u32 k = 0; k < 3; ++k) ed.f[k] = (k < new_count) ? s_out[swz(k)] : TOK_SENTINEL;
-                ed.l[1] = new_count >= 1 ? s_out[swz(new_count - 1)] : TOK_SENTINEL;
-                ed.l[0] = new_count >= 2 ? s_out[swz(new_count - 2)] : TOK_SENTINEL;
-                ed.pad[0] = ed.pad[1] = 0;
-                e_next[seg] = ed;
+                pend_seg = seg; pend_count = new_count; pend_par = j & 1u; pending = true;
                 cta_drops += count - new_count;
             }
         }
         named_bar_sync(1, MS_CTHREADS);
+        if (tid == 0) flush_edge();
         if (A.delta)
             for (u32 i = tid; i < MS_DCACHE; i += MS_CTHREADS)
                 if (s_dkey[i] != 0xffffffffu && s_dcnt[i]) atomicAdd(&A.delta[s_dkey[i]], (ull)s_dcnt[i]);
