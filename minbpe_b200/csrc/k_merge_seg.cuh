@@ -345,7 +345,9 @@ __global__ void __launch_bounds__(MS_THREADS, MS_MINBLOCKS) k_merge_seg(SegArgs 
 #pragma unroll
                     for (int r = 0; r < 4; ++r) {
                         u32 dst = woff + rowoff[r] + lpre[r];
-                        if (keep[r] == 0xfu && mn[r] == 0) {
+                        // warp-uniform choice per row: a row without any change takes the 4-word path,
+                        // otherwise every lane takes the per-token path (no divergent double execution)
+                        if (!__any_sync(0xffffffffu, keep[r] != 0xfu || mn[r] != 0)) {
                             if ((dst & 3u) == 0) {
                                 *reinterpret_cast<uint4 *>(s_out + swz(dst)) = make_uint4(t[r][0], t[r][1], t[r][2], t[r][3]);
                             } else {
