@@ -24,7 +24,7 @@
 // Tuned on B200 (profiles/r1_summary.md §5): 2 stages x 16 KB + 16 KB staging + 4 KB delta cache =
 // 53 KB -> 4 CTAs/SM at 56 registers (36 warps) beat 3 stages / 3 CTAs by 8 %.
 #ifndef MS_STAGES
-#define MS_STAGES 2
+#define MS_STAGES 3
 #endif
 #ifndef MS_MINBLOCKS
 #define MS_MINBLOCKS 4
@@ -34,9 +34,8 @@
 #endif
 #define MS_PAD 4                            // body starts at word 4 of a stage (16-byte aligned)
 #define MS_IN_WORDS (SEG_TOKENS + 8)
-#define MS_OUT_WORDS (SEG_TOKENS + 8)
 #define MS_DCACHE (1 << MS_DCACHE_LOG2)     // slots of the per-CTA delta cache (shared memory)
-#define MS_SMEM_BYTES (MS_STAGES * MS_IN_WORDS * 4 + MS_OUT_WORDS * 4 + MS_DCACHE * 8 + 640)
+#define MS_SMEM_BYTES (MS_STAGES * MS_IN_WORDS * 4 + MS_DCACHE * 8 + 640)
 #define MS_INVALID 0xffffffffu
 
 
@@ -83,11 +82,6 @@ __device__ __noinline__ void delta_one(const u32 *s, const u32 *h, u32 count, in
         delta_cache_add(s_dkey, s_dcnt, delta, m_p2 ? 2u * V : V + tp2);
 }
 
-// staging-tile swizzle at 16-byte granularity: word i lives in group (i>>2) ^ ((i>>5) & 7).  The
-// stride-4 scatter of the compaction (lane l writes word d+4l) and the 16-byte copy-out reads are
-// both bank-conflict free under it.
-__device__ __forceinline__ u32 swz(u32 i) { const u32 g = i >> 2; return ((g ^ ((g >> 3) & 7u)) << 2) | (i & 3u); }
-
 struct SegArgs {
     Ctl *ctl;
     u32 *buf0, *buf1;
@@ -104,8 +98,7 @@ __global__ void __launch_bounds__(MS_THREADS, MS_MINBLOCKS) k_merge_seg(SegArgs 
 
     extern __shared__ __align__(128) unsigned char smem_raw[];
     u32 *s_in = reinterpret_cast<u32 *>(smem_raw);                    // [MS_STAGES][MS_IN_WORDS]
-    u32 *s_out = s_in + MS_STAGES * MS_IN_WORDS;                      // [MS_OUT_WORDS]
-    u64 *s_full = reinterpret_cast<u64 *>(s_out + MS_OUT_WORDS);      // [MS_STAGES]
+    u64 *s_full = reinterpret_cast<u64 *>(s_in + MS_STAGES * MS_IN_WORDS);   // [MS_STAGES]
     u64 *s_empty = s_full + MS_STAGES;                                // [MS_STAGES]
     u32 *s_seg = reinterpret_cast<u32 *>(s_empty + MS_STAGES);        // [MS_STAGES] segment id or MS_INVALID
     u32 *s_cnt = s_seg + MS_STAGES;                                   // [MS_STAGES]
@@ -165,17 +158,20 @@ __global__ void __launch_bounds__(MS_THREADS, MS_MINBLOCKS) k_merge_seg(SegArgs 
         ull cta_drops = 0;  // meaningful in thread 0
         // thread 0: the edge record of the previous changed segment is assembled one barrier later,
         // when every warp has finished its copy-out and deposited the boundary tokens in s_edge
-        bool pending = false; u32 pend_seg = 0, pend_count = 0, pend_par = 0;
-        auto flush_edge = [&]() {
-            if (!pending) return;
-            const u32 *se = s_edge + pend_par * 8;
-            Edge ed;
-            ed.count = pend_count;
-            for (u32 k = 0; k < 3; ++k) ed.f[k] = (k < pend_count) ? se[k] : TOK_SENTINEL;
-            ed.l[0] = pend_count >= 2 ? se[3] : TOK_SENTINEL;
-            ed.l[1] = pend_count >= 1 ? se[4] : TOK_SENTINEL;
-            ed.pad[0] = ed.pad[1] = 0;
-            e_next[pend_seg] = ed;
+        bool pending = false; u32 pend_par = 0;   // thread 0 only
+        auto flush_edge = [&]() {   // called by warp 0 right after a block barrier
+            const u32 par = __shfl_sync(0xffffffffu, pending ? pend_par + 1u : 0u, 0);
+            if (!par) return;
+            const u32 *se = s_edge + (par - 1u) * 8;
+            const u32 cnt = se[5], sg = se[6];
+            if (lane < 8) {
+                u32 word = 0;
+                if (lane < 3) word = (lane < cnt) ? se[lane] : TOK_SENTINEL;
+                else if (lane == 3) word = cnt >= 2 ? se[3] : TOK_SENTINEL;
+                else if (lane == 4) word = cnt >= 1 ? se[4] : TOK_SENTINEL;
+                else if (lane == 5) word = cnt;
+                reinterpret_cast<u32 *>(&e_next[sg])[lane] = word;   // Edge = f[3], l[2], count, pad[2]
+            }
             pending = false;
         };
         for (u32 j = 0;; ++j) {
@@ -190,7 +186,7 @@ __global__ void __launch_bounds__(MS_THREADS, MS_MINBLOCKS) k_merge_seg(SegArgs 
             // token i of the segment extended by its neighbours (i in [-2, count+3))
             auto tok = [&](int i) -> u32 { return seg_tok(s, h, count, i); };
 
-            u32 t[4][4], mn[4], keep[4], lpre[4], rowoff[4];
+            u32 t[4][4], mn[4], keep[4], lpre[4], rowoff[4], rowcnt[4];
             u32 wtot = 0, many = 0;
             bool plain = true;   // warp-uniform: no token of this warp's span is removed or replaced
             const u32 wbase = warp * MS_WSPAN;
@@ -279,7 +275,7 @@ __global__ void __launch_bounds__(MS_THREADS, MS_MINBLOCKS) k_merge_seg(SegArgs 
                 many = __any_sync(0xffffffffu, many != 0) ? 1u : 0u;
                 if (!__any_sync(0xffffffffu, rem_any != 0)) {
 #pragma unroll
-                    for (int r = 0; r < 4; ++r) { lpre[r] = 4 * lane; rowoff[r] = 128 * r; }
+                    for (int r = 0; r < 4; ++r) { lpre[r] = 4 * lane; rowoff[r] = 128 * r; rowcnt[r] = 128; }
                     wtot = MS_WSPAN;
                     plain = (many == 0);
                 } else {
@@ -292,26 +288,38 @@ __global__ void __launch_bounds__(MS_THREADS, MS_MINBLOCKS) k_merge_seg(SegArgs 
                         rowoff[r] = run;
                         if (!__any_sync(0xffffffffu, keep[r] != 0xfu)) {   // row keeps all of its 128 tokens
                             lpre[r] = 4 * lane;
+                            rowcnt[r] = 128;
                             run += 128;
                         } else {
                             const u32 gone = 4u - __popc(keep[r]);
                             const u32 b0 = __ballot_sync(0xffffffffu, gone & 1u), b1 = __ballot_sync(0xffffffffu, gone & 2u),
                                       b2 = __ballot_sync(0xffffffffu, gone & 4u);
                             lpre[r] = 4 * lane - (__popc(b0 & lt) + 2 * __popc(b1 & lt) + 4 * __popc(b2 & lt));
-                            run += 128 - (__popc(b0) + 2 * __popc(b1) + 4 * __popc(b2));
+                            rowcnt[r] = 128 - (__popc(b0) + 2 * __popc(b1) + 4 * __popc(b2));
+                            run += rowcnt[r];
                         }
                     }
                     wtot = run;
                 }
             } else {
 #pragma unroll
-                for (int r = 0; r < 4; ++r) { mn[r] = 0; keep[r] = 0; lpre[r] = 0; rowoff[r] = 0; }
+                for (int r = 0; r < 4; ++r) { mn[r] = 0; keep[r] = 0; lpre[r] = 0; rowoff[r] = 0; rowcnt[r] = 0; }
+            }
+            // ---- statistics delta of this warp's merge starts (reads the stage before anyone rewrites it) ----
+            if (A.delta && many) {
+                u32 mall = mn[0] | (mn[1] << 4) | (mn[2] << 8) | (mn[3] << 12);
+#pragma unroll 1
+                while (mall) {   // one pass per merge start of this lane
+                    const int bit = __ffs(mall) - 1;
+                    mall &= mall - 1;
+                    delta_one(s, h, count, (int)(wbase + (bit >> 2) * 128 + lane * 4 + (bit & 3)), a, b, A.V, s_dkey, s_dcnt, A.delta);
+                }
             }
             // bit 31 of the warp total = "this warp replaces a token" (a merge whose tail lies in
             // the next warp / segment changes a token without removing one)
             if (lane == 0) s_wtot[warp] = wtot | (many << 31);
-            named_bar_sync(1, MS_CTHREADS);  // (1) warp totals visible; staging tile free; previous copy-out done
-            if (tid == 0) flush_edge();
+            named_bar_sync(1, MS_CTHREADS);  // (1) warp totals visible; nobody reads another warp's span of the stage any more
+            if (warp == 0) flush_edge();
 
             u32 woff = 0, new_count = 0, chg = 0;
 #pragma unroll
@@ -330,81 +338,68 @@ __global__ void __launch_bounds__(MS_THREADS, MS_MINBLOCKS) k_merge_seg(SegArgs 
                 continue;
             }
 
-            if (wbase < count) {
-                if (plain) {   // whole warp keeps its 512 tokens unchanged: straight 16-byte copies
+            // ---- compact in place, row by row, inside the stage; clean rows are left as they are ----
+            u32 *sw = s_in + stage * MS_IN_WORDS + MS_PAD;
+            if (wtot | many) {
 #pragma unroll
-                    for (int r = 0; r < 4; ++r) {
-                        const u32 dst = woff + 128 * r + 4 * lane;
-                        if ((dst & 3u) == 0) {
-                            *reinterpret_cast<uint4 *>(s_out + swz(dst)) = make_uint4(t[r][0], t[r][1], t[r][2], t[r][3]);
-                        } else {
-                            s_out[swz(dst)] = t[r][0]; s_out[swz(dst + 1)] = t[r][1]; s_out[swz(dst + 2)] = t[r][2]; s_out[swz(dst + 3)] = t[r][3];
-                        }
-                    }
-                } else {
+                for (int r = 0; r < 4; ++r) {
+                    if (__any_sync(0xffffffffu, keep[r] != 0xfu || mn[r] != 0)) {
+                        u32 dst = wbase + r * 128 + lpre[r];
 #pragma unroll
-                    for (int r = 0; r < 4; ++r) {
-                        u32 dst = woff + rowoff[r] + lpre[r];
-                        // warp-uniform choice per row: a row without any change takes the 4-word path,
-                        // otherwise every lane takes the per-token path (no divergent double execution)
-                        if (!__any_sync(0xffffffffu, keep[r] != 0xfu || mn[r] != 0)) {
-                            if ((dst & 3u) == 0) {
-                                *reinterpret_cast<uint4 *>(s_out + swz(dst)) = make_uint4(t[r][0], t[r][1], t[r][2], t[r][3]);
-                            } else {
-                                s_out[swz(dst)] = t[r][0]; s_out[swz(dst + 1)] = t[r][1]; s_out[swz(dst + 2)] = t[r][2]; s_out[swz(dst + 3)] = t[r][3];
+                        for (int k = 0; k < 4; ++k) {
+                            if ((keep[r] >> k) & 1u) {
+                                sw[dst] = ((mn[r] >> k) & 1u) ? (z | (t[r][k] & TOK_FLAG)) : t[r][k];
+                                ++dst;
                             }
-                        } else {
-#pragma unroll
-                            for (int k = 0; k < 4; ++k) {
-                                if ((keep[r] >> k) & 1u) {
-                                    s_out[swz(dst)] = ((mn[r] >> k) & 1u) ? (z | (t[r][k] & TOK_FLAG)) : t[r][k];
-                                    ++dst;
-                                }
-                            }
-                        }
-                    }
-                    if (A.delta && many) {
-                        u32 mall = mn[0] | (mn[1] << 4) | (mn[2] << 8) | (mn[3] << 12);
-#pragma unroll 1
-                        while (mall) {   // one pass per merge start of this lane
-                            const int bit = __ffs(mall) - 1;
-                            mall &= mall - 1;
-                            delta_one(s, h, count, (int)(wbase + (bit >> 2) * 128 + lane * 4 + (bit & 3)), a, b, A.V,
-                                      s_dkey, s_dcnt, A.delta);
                         }
                     }
                 }
-            }
-            __syncwarp();   // the warp's own range [woff, woff + wtot) of the staging tile is complete
-            if (lane == 0) mbar_arrive(&s_empty[stage]);   // this warp no longer reads the input stage
-
-            // ---- copy-out, warp by warp (no second block barrier): every warp streams its own range of
-            // the compacted segment; whole 16-byte groups go as vectors (segment base is 16 KB aligned),
-            // the ragged ends shared with the neighbouring warps' ranges as single words ----
-            if (wtot) {
+                __syncwarp();
+                // ---- copy-out: row r holds rowcnt[r] tokens at the start of its 128-word slot ----
                 u32 *__restrict__ segp = w + (u64)seg * SEG_TOKENS;
-                const u32 lo = woff, hi = woff + wtot;
-                const u32 v0 = (lo + 3u) >> 2, v1 = hi >> 2;   // groups fully inside [lo, hi)
-                if (v1 > v0) {
-                    for (u32 v = v0 + lane; v < v1; v += 32)
-                        reinterpret_cast<uint4 *>(segp)[v] = reinterpret_cast<const uint4 *>(s_out)[v ^ ((v >> 3) & 7u)];
-                    if (lane < 3) { const u32 i = lo + lane; if (i < 4 * v0) segp[i] = s_out[swz(i)]; }            // head
-                    else if (lane < 6) { const u32 i = 4 * v1 + (lane - 3); if (i < hi) segp[i] = s_out[swz(i)]; }  // tail
-                } else {
-                    for (u32 i = lo + lane; i < hi; i += 32) segp[i] = s_out[swz(i)];
+#pragma unroll
+                for (int r = 0; r < 4; ++r) {
+                    const u32 c = rowcnt[r];
+                    if (c) {
+                        const u32 gdst = woff + rowoff[r];
+                        const u32 *sp = sw + wbase + r * 128;
+                        u32 *gp = segp + gdst;
+                        if ((gdst & 3u) == 0) {   // 16-byte aligned on both sides
+                            if (4 * lane + 4 <= c) reinterpret_cast<uint4 *>(gp)[lane] = reinterpret_cast<const uint4 *>(sp)[lane];
+                            else {
+#pragma unroll
+                                for (int k = 0; k < 4; ++k) if (4 * lane + k < c) gp[4 * lane + k] = sp[4 * lane + k];
+                            }
+                        } else {
+#pragma unroll
+                            for (int q = 0; q < 4; ++q) { const u32 i = 32 * q + lane; if (i < c) gp[i] = sp[i]; }
+                        }
+                    }
                 }
-                // tokens of the new edge record that fall into this warp's range
-                u32 *se = s_edge + (j & 1u) * 8;
-                if (lane < 3) { const u32 i = lane; if (i >= lo && i < hi) se[lane] = s_out[swz(i)]; }
-                else if (lane < 5) { const u32 back = 5 - lane; if (new_count >= back) { const u32 i = new_count - back; if (i >= lo && i < hi) se[lane] = s_out[swz(i)]; } }
+                // boundary tokens of the new segment that live in this warp's rows -> s_edge
+                if (lane < 5) {
+                    const u32 back = 5 - lane;   // lanes 3,4: positions new_count-2, new_count-1
+                    const bool want = lane < 3 ? (lane < new_count) : (new_count >= back);
+                    const u32 p = lane < 3 ? lane : new_count - back;
+                    if (want && p >= woff && p < woff + wtot) {
+                        const u32 q = p - woff;
+                        const int r = (q >= rowoff[3]) ? 3 : (q >= rowoff[2]) ? 2 : (q >= rowoff[1]) ? 1 : 0;
+                        const u32 ro = r == 3 ? rowoff[3] : r == 2 ? rowoff[2] : r == 1 ? rowoff[1] : rowoff[0];
+                        s_edge[(j & 1u) * 8 + lane] = sw[wbase + r * 128 + (q - ro)];
+                    }
+                }
             }
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&s_empty[stage]);   // this warp is done with the stage
             if (tid == 0) {
-                pend_seg = seg; pend_count = new_count; pend_par = j & 1u; pending = true;
+                u32 *se = s_edge + (j & 1u) * 8;
+                se[5] = new_count; se[6] = seg; se[7] = 1u;
+                pend_par = j & 1u; pending = true;
                 cta_drops += count - new_count;
             }
         }
         named_bar_sync(1, MS_CTHREADS);
-        if (tid == 0) flush_edge();
+        if (warp == 0) flush_edge();
         if (A.delta)
             for (u32 i = tid; i < MS_DCACHE; i += MS_CTHREADS)
                 if (s_dkey[i] != 0xffffffffu && s_dcnt[i]) atomicAdd(&A.delta[s_dkey[i]], (ull)s_dcnt[i]);
