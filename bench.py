@@ -35,6 +35,17 @@ sys.path.insert(0, ROOT)
 GPT4 = r"""'(?i:[sdmt]|ll|ve|re)|[^\r\n\p{L}\p{N}]?+\p{L}+|\p{N}{1,3}| ?[^\s\p{L}\p{N}]++[\r\n]*|\s*[\r\n]|\s+(?!\S)|\s+"""
 
 
+def ncu_traffic():
+    """DRAM bytes of one profiled launch of the dominant kernel (ncu --set full, committed under profiles/);
+    null when no capture of the current kernel is on record."""
+    p = os.path.join(ROOT, "profiles", "ncu_traffic.json")
+    try:
+        d = json.load(open(p))
+        return d["dram_bytes"], d
+    except Exception:  # noqa: BLE001
+        return None, None
+
+
 def measured_peak():
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(p):
@@ -261,7 +272,8 @@ def run_ours(args):
         "gpu_launches": int(tm["kernel_launches"]),
         "clocks": clocks,
         "roofline": {"bound": "hbm", "kernel": "k_merge_seg (fused merge + in-place segment compaction + stats delta)",
-                     "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": None,
+                     "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": ncu_traffic()[0],
+                     "traffic_capture": ncu_traffic()[1],
                      "peak_source": peak_src, "bytes_per_launch": (4.0 * n_in + 4.0 * n_out) / K, "ms_per_launch": k_ms,
                      "loop_frac_in_kernel": tm["merge_kernel_ms"] / tm["loop_ms"]},
         "cpu_baseline": cpu,
@@ -295,6 +307,14 @@ def run_extras(args):
     raw = generate(1339, size)
     offs = chunk_offsets(GPT4, raw)
     eng = E.Engine(0)
+    # a longer stretch of the cfg3 loop: dense early merges, sparse later ones, pairs (a,a), re-packing
+    eng.load_stream(raw, offs)
+    t0 = time.perf_counter(); mp, mc, md = eng.train(1024); torch.cuda.synchronize(); dt = time.perf_counter() - t0
+    tm = eng.timing()
+    out["train_1024"] = {"bytes": size, "merges": int(md), "wall_s": dt, "loop_ms": tm["loop_ms"], "init_ms": tm["init_ms"],
+                         "merges_per_s": md / (tm["loop_ms"] / 1e3), "tokens_in_sum": tm["tokens_in"], "tokens_out_sum": tm["tokens_out"],
+                         "stream_GBps": 4.0 * tm["tokens_in"] / (tm["loop_ms"] / 1e3) / 1e9, "same_pairs": int(sum(1 for a, b in mp.tolist() if a == b)),
+                         "table_slots": tm["table_slots"], "final_tokens": int(eng.stream_len())}
     eng.load_stream(raw[: 64 << 20], offs[: int(np.searchsorted(offs, 64 << 20))])
     merges, _, done = eng.train(2048)
     torch.cuda.synchronize()

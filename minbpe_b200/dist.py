@@ -235,3 +235,19 @@ def bench_sharded(args, rank, world, local):
         print(json.dumps(line), flush=True)
     eng.close()
     dist.destroy_process_group()
+
+
+def encode_sharded(engine, data, offsets, merges, byte_perm=None, group=None, gather=False):
+    """regex.py:111-121 over `world` GPUs: chunks are independent, so encode needs no exchange at all —
+    every rank encodes its contiguous chunk range (replicas over byte-range shards).  Returns this
+    rank's ids; with gather=True rank 0 also gets the concatenation in text order (others: None)."""
+    rank, world = dist.get_rank(group), dist.get_world_size(group)
+    raw = np.frombuffer(data, dtype=np.uint8) if not isinstance(data, np.ndarray) else data
+    blo, bhi, clo, chi = shard_chunks(raw.size, offsets, rank, world)
+    local_offs = np.asarray(offsets[clo:chi], dtype=np.uint64) - np.uint64(blo)
+    ids = engine.encode(raw[blo:bhi], local_offs if len(local_offs) else None, merges, byte_perm) if bhi > blo else np.zeros(0, np.int32)
+    if not gather:
+        return ids
+    parts = [None] * world if rank == 0 else None
+    dist.gather_object(ids, parts, dst=0, group=group)
+    return np.concatenate(parts) if rank == 0 else None
