@@ -208,8 +208,10 @@ def bench_sharded(args, rank, world, local):
         from bench import measured_peak
         t = float(t_loop.item())
         peak, peak_src = measured_peak()
-        # timing counters cover the whole W+K run of this rank; the per-launch figures use all of them
-        k_ms = tm["merge_kernel_ms"] / max(n, 1)
+        # token counters cover the whole W+K run of rank 0.  The per-launch time is taken from the step time
+        # (merge pass + arg-max + both collectives), i.e. a lower bound on the kernel's own rate: CUDA events
+        # around single launches are not meaningful on a stream that NCCL work is interleaved with.
+        k_ms = t / K * 1e3
         bytes_per_launch = 4.0 * (tm["tokens_in"] + tm["tokens_out"]) / max(n, 1)
         line = {
             "metric": "train_loop_corpus_GBps", "value": size * world * K / t / 1e9, "unit": "GB/s", "n_gpus": world,
@@ -223,7 +225,7 @@ def bench_sharded(args, rank, world, local):
                        "timing": "CUDA events on the shared torch stream, max over ranks, barrier + synchronize on both sides"},
             "merges_per_s": K / t, "wall_ms_per_step": wall / K * 1e3,
             "gpu_launches": int(tm["kernel_launches"]),
-            "roofline": {"bound": "hbm", "kernel": "k_merge_seg (rank 0)", "achieved": bytes_per_launch / (k_ms / 1e3) / 1e9,
+            "roofline": {"bound": "hbm", "kernel": "k_merge_seg (rank 0; rate over the whole step incl. collectives)", "achieved": bytes_per_launch / (k_ms / 1e3) / 1e9,
                          "peak": peak, "unit": "GB/s", "frac": bytes_per_launch / (k_ms / 1e3) / 1e9 / peak, "traffic": None,
                          "peak_source": peak_src, "ms_per_launch": k_ms},
             "cpu_baseline": None,
