@@ -315,6 +315,17 @@ def run_extras(args):
                          "merges_per_s": md / (tm["loop_ms"] / 1e3), "tokens_in_sum": tm["tokens_in"], "tokens_out_sum": tm["tokens_out"],
                          "stream_GBps": 4.0 * tm["tokens_in"] / (tm["loop_ms"] / 1e3) / 1e9, "same_pairs": int(sum(1 for a, b in mp.tolist() if a == b)),
                          "table_slots": tm["table_slots"], "final_tokens": int(eng.stream_len())}
+    # the literal two-pass loop of the north star (full pair histogram every iteration: BPE_OPT_RESCAN)
+    sub = 256 << 20
+    eng.load_stream(raw[:sub], offs[: int(np.searchsorted(offs, sub))])
+    eng.set_option(E.OPT_RESCAN, 1); eng.set_option(E.OPT_KERNEL_TIMING, 1)
+    eng.train(3)
+    _, _, rd = eng.train(8, first_idx=259)
+    tr = eng.timing()
+    eng.set_option(E.OPT_RESCAN, 0); eng.set_option(E.OPT_KERNEL_TIMING, 0)
+    hist_ms = (tr["loop_ms"] - tr["merge_kernel_ms"]) / max(rd, 1)
+    out["rescan_256MiB"] = {"merges": int(rd), "loop_ms_per_merge": tr["loop_ms"] / max(rd, 1), "merge_ms": tr["merge_kernel_ms"] / max(rd, 1),
+                            "hist_argmax_ms": hist_ms, "hist_GBps": 4.0 * tr["tokens_in"] / max(rd, 1) / (hist_ms / 1e3) / 1e9}
     eng.load_stream(raw[: 64 << 20], offs[: int(np.searchsorted(offs, 64 << 20))])
     merges, _, done = eng.train(2048)
     torch.cuda.synchronize()

@@ -423,6 +423,10 @@ extern "C" int bpe_get_stats(bpe_handle *h, int32_t *pairs, int64_t *counts, uin
     Table t;
     if ((rc = alloc_table(h, t, tcap, true))) { free_table(h, t); return rc; }
     const u64 used_before = h->h_ctl->table_used;
+    {   // the scratch table counts its own occupancy (k_hist_hash refuses inserts near a full table)
+        const ull zero = 0;
+        CU(cudaMemcpyAsync(&h->ctl->table_used, &zero, 8, cudaMemcpyHostToDevice, h->stream));
+    }
     k_hist_hash<<<h->sms * 8, 256, 0, h->stream>>>(h->buf[0], h->buf[1], h->ctl, h->edge[0], h->edge[1], t, 0);
     std::vector<u64> keys(tcap), cnt(tcap), first(tcap);
     cudaError_t e = cudaMemcpyAsync(keys.data(), t.keys, tcap * 8, cudaMemcpyDeviceToHost, h->stream);
@@ -608,7 +612,8 @@ static void enqueue_iteration(bpe_handle *h) {
         // verification mode: rebuild the histogram from the stream, no incremental update
         cudaMemsetAsync(h->table.keys, 0xff, (h->table.mask + 1) * 8, h->stream);
         cudaMemsetAsync(h->table.counts, 0, (h->table.mask + 1) * 8, h->stream);
-        k_hist_hash<<<h->sms * 8, 256, 0, h->stream>>>(h->buf[0], h->buf[1], h->ctl, h->edge[0], h->edge[1], h->table, 1);
+        cudaMemsetAsync(&h->ctl->table_used, 0, 8, h->stream);
+        k_hist_hash<<<h->sms * 4, 256, 0, h->stream>>>(h->buf[0], h->buf[1], h->ctl, h->edge[0], h->edge[1], h->table, 1);
         h->tm.kernel_launches++;
     }
     k_argmax<<<h->argmax_grid, 256, 0, h->stream>>>(h->table, h->ctl, h->partials, h->log_pairs, h->log_counts);
@@ -651,7 +656,11 @@ extern "C" int bpe_train(bpe_handle *h, int32_t num_merges, int32_t first_idx, i
     // ---- initial statistics (the only full histogram of the run) ----
     CU(cudaEventRecord(ev0, h->stream));
     // only a non-byte stream (bpe_load_ids) or the rescan mode insert without the load check
-    u64 cap = auto_table_cap(h, (h->opt_rescan || !h->bytes_only) ? h->h_ctl->n : 0);
+    u64 cap = auto_table_cap(h, !h->bytes_only ? h->h_ctl->n : 0);
+    if (h->opt_rescan && !h->opt_table_log2) {   // every iteration clears and rescans: keep the table moderate
+        cap = 1ull << 20;
+        while (cap < h->h_ctl->n / 16 && cap < (1ull << 26)) cap <<= 1;
+    }
     const bool reuse = h->table_valid && h->table.keys && !h->opt_rescan;  // continuing a previous bpe_train
     if (!reuse && (rc = build_table(h, cap))) return rc;
     h->table_valid = false;  // becomes true again when the loop ends cleanly
@@ -676,7 +685,10 @@ extern "C" int bpe_train(bpe_handle *h, int32_t num_merges, int32_t first_idx, i
         CU(cudaGetLastError());
         if ((rc = pull_ctl(h))) return rc;
         drain_kernel_events(h);
-        if (h->h_ctl->overflow && (rc = handle_overflow(h))) return rc;
+        if (h->h_ctl->overflow) {
+            if (h->opt_rescan) return fail(h, BPE_ERR_CAPACITY, "rescan mode: pair table too small (set BPE_OPT_TABLE_LOG2)");
+            if ((rc = handle_overflow(h))) return rc;
+        }
         done_iters = (int)h->h_ctl->iter;
         exhausted = h->h_ctl->done != 0;
     }

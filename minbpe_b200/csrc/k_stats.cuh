@@ -101,10 +101,28 @@ __global__ void k_dense_to_table(const ull *__restrict__ dense, Table t, Ctl *ct
 }
 
 // Arbitrary stream -> hash table with first-occurrence positions (count += 1, first = min).  This
-// is get_stats() (base.py:13-22) for the C ABI and the "rescan" verification mode.
+// is get_stats() (base.py:13-22) for the C ABI and the "rescan" verification mode: the scan the
+// north star describes — 16-byte loads, equal keys of a warp folded with __match_any_sync, a
+// per-block open-addressing histogram {pair, count, first position} in shared memory, one flush of
+// every block's table into the global one (device-wide combine); keys that do not find a slot
+// within a few probes go to the global table directly.
+#define HH_SLOTS 2048
+__device__ __forceinline__ void hist_global_add(Table &tab, Ctl *ctl, u64 key, ull add, u64 pos) {
+    // a full histogram inserts without reservations: refuse (and flag) rather than fill the table up
+    if (*(volatile ull *)&ctl->table_used >= (3 * (tab.mask + 1)) / 4) { ctl->overflow = 1; return; }
+    const u64 slot = table_upsert(tab, key, &ctl->table_used);
+    atomicAdd((ull *)&tab.counts[slot], add);
+    if (tab.first) atomicMin((ull *)&tab.first[slot], (ull)pos);
+}
+
 __global__ void __launch_bounds__(256) k_hist_hash(const u32 *__restrict__ buf0, const u32 *__restrict__ buf1,
                                                    Ctl *ctl, const Edge *e0, const Edge *e1, Table tab, int gated) {
     if (gated && (ctl->done || ctl->overflow || ctl->iter >= ctl->max_iter)) return;
+    __shared__ ull s_key[HH_SLOTS];
+    __shared__ ull s_first[HH_SLOTS];
+    __shared__ u32 s_cnt[HH_SLOTS];
+    for (u32 i = threadIdx.x; i < HH_SLOTS; i += blockDim.x) { s_key[i] = KEY_EMPTY; s_first[i] = POS_NONE; s_cnt[i] = 0; }
+    __syncthreads();
     const u32 *__restrict__ w = ctl->cur ? buf1 : buf0;
     const Edge *e = edges_cur(ctl, e0, e1);
     const u32 nseg = ctl->nseg;
@@ -120,13 +138,32 @@ __global__ void __launch_bounds__(256) k_hist_hash(const u32 *__restrict__ buf0,
                 const u32 peers = __match_any_sync(__activemask(), key);
                 // the lowest lane of a group also holds the group's smallest position
                 if (valid && (__ffs(peers) - 1) == (int)lane_id()) {
-                    const u64 slot = table_upsert(tab, key, &ctl->table_used);
-                    atomicAdd((ull *)&tab.counts[slot], (ull)__popc(peers));
-                    if (tab.first) atomicMin((ull *)&tab.first[slot], (ull)((u64)t * SEG_TOKENS + i0 + k));
+                    const u32 add = __popc(peers);
+                    const u64 pos = (u64)t * SEG_TOKENS + i0 + k;
+                    u32 slot = (u32)(hash64(key) & (HH_SLOTS - 1));
+                    bool placed = false;
+#pragma unroll 1
+                    for (int probe = 0; probe < 6 && !placed; ++probe) {
+                        ull kk = reinterpret_cast<volatile ull *>(s_key)[slot];
+                        if (kk == KEY_EMPTY) {
+                            const ull old = atomicCAS(&s_key[slot], (ull)KEY_EMPTY, (ull)key);
+                            kk = (old == KEY_EMPTY) ? key : old;
+                        }
+                        if (kk == key) {
+                            atomicAdd(&s_cnt[slot], add);
+                            atomicMin(&s_first[slot], (ull)pos);
+                            placed = true;
+                        }
+                        slot = (slot + 1) & (HH_SLOTS - 1);
+                    }
+                    if (!placed) hist_global_add(tab, ctl, key, add, pos);
                 }
             }
         }
     }
+    __syncthreads();
+    for (u32 i = threadIdx.x; i < HH_SLOTS; i += blockDim.x)
+        if (s_key[i] != KEY_EMPTY && s_cnt[i]) hist_global_add(tab, ctl, s_key[i], s_cnt[i], s_first[i]);
 }
 
 // =============================================================================================
