@@ -115,6 +115,21 @@ int bpe_encode(bpe_handle *h, const uint8_t *bytes, uint64_t n,
                const int32_t *merges, int32_t n_merges, const uint8_t *byte_perm,
                int32_t *out_ids, uint64_t out_cap, uint64_t *out_n);
 
+/* ---- the GPT-4 split pattern on the device (regex.py:19, used at regex.py:41 and :114) -------- */
+/* `re.findall(GPT4_SPLIT_PATTERN, text)` as scans + element-wise kernels (k_split.cuh; the rules are
+ * pinned against the `regex` module by tests/test_split_rules.py).  The caller provides the Unicode
+ * class table of the regex engine it wants to match (minbpe_b200/unicode_tables.py enumerates the
+ * installed `regex` module): cls_table[cp] in {0 letter, 1 number, 2 CR/LF, 3 other whitespace,
+ * 4 apostrophe, 5 other} for cp < 0x110000, contr_table[cp] (cp < 0x3000) = bit0 (?i:[sdmt]),
+ * bit1 (?i:l), bit2 (?i:v), bit3 (?i:e), bit4 (?i:r). */
+int bpe_gpt4_tables(bpe_handle *h, const uint8_t *cls_table, const uint8_t *contr_table);
+/* Chunk start offsets (bytes) of valid UTF-8 `bytes` under the GPT-4 pattern. */
+int bpe_split_gpt4(bpe_handle *h, const uint8_t *bytes, uint64_t n, uint64_t *out_offsets, uint64_t cap,
+                   uint64_t *n_chunks);
+/* regex.py:41-44 without the host: upload + split + widen; same stream as
+ * bpe_load_stream(bytes, n, <offsets of the regex chunks>).  n_chunks may be NULL. */
+int bpe_load_text_gpt4(bpe_handle *h, const uint8_t *bytes, uint64_t n, uint64_t *n_chunks);
+
 /* ---- step-wise training: the sharded (multi-GPU) loop ---------------------------------------- */
 /* One process per GPU, each holding a contiguous shard of the corpus (cut at chunk starts) and an
  * identical copy of the global pair-count table.  Per merge the host (minbpe_b200/dist.py) issues

@@ -18,6 +18,7 @@
 #include "k_seg.cuh"
 #include "k_stats.cuh"
 #include "k_encode.cuh"
+#include "k_split.cuh"
 
 #define BPE_ABI_VERSION 1
 
@@ -46,6 +47,7 @@ struct bpe_handle {
     u32 *d_err = nullptr;
     int *log_pairs = nullptr; long long *log_counts = nullptr; int log_cap = 0;
     Best *partials = nullptr;
+    unsigned char *d_cls = nullptr, *d_contr = nullptr;   // code-point class / contraction tables of the GPT-4 splitter
     int argmax_grid = 0, merge_grid = 0, merge_grid_same = 0, merge_grid_seg = 0, ff_grid = 0;
 
     // options
@@ -178,6 +180,8 @@ extern "C" int bpe_destroy(bpe_handle *h) {
     if (h->log_pairs) cudaFree(h->log_pairs);
     if (h->log_counts) cudaFree(h->log_counts);
     if (h->partials) cudaFree(h->partials);
+    if (h->d_cls) cudaFree(h->d_cls);
+    if (h->d_contr) cudaFree(h->d_contr);
     if (h->ctl) cudaFree(h->ctl);
     if (h->h_ctl) cudaFreeHost(h->h_ctl);
     if (h->own_stream) cudaStreamDestroy(h->own_stream);
@@ -735,3 +739,4 @@ extern "C" int bpe_debug_table(bpe_handle *h, int32_t *pairs, int64_t *counts, u
 
 #include "encode_host.inl"
 #include "step_host.inl"
+#include "split_host.inl"

@@ -59,6 +59,9 @@ def load_library():
         "bpe_get_timing": ([vp, P(Timing)], ci),
         "bpe_set_option": ([vp, ci, i64], ci),
         "bpe_debug_table": ([vp, vp, vp, u64, P(u64)], ci),
+        "bpe_gpt4_tables": ([vp, vp, vp], ci),
+        "bpe_split_gpt4": ([vp, vp, u64, vp, u64, P(u64)], ci),
+        "bpe_load_text_gpt4": ([vp, vp, u64, P(u64)], ci),
         "bpe_set_stream": ([vp, vp], ci),
         "bpe_step_begin": ([vp, vp], ci),
         "bpe_step_table": ([vp, vp, i32, i32, i32], ci),
@@ -201,6 +204,33 @@ class Engine:
                 continue
             self._check(rc, "bpe_debug_table")
             return {(int(p[0]), int(p[1])): int(c) for p, c in zip(pairs[: n.value], counts[: n.value])}
+
+    # ---- GPT-4 split pattern on the device ----
+    def _ensure_gpt4_tables(self):
+        if not getattr(self, "_gpt4_ready", False):
+            from .unicode_tables import tables
+            cls, contr = tables()
+            self._check(self._lib.bpe_gpt4_tables(self._h, _ptr(cls), _ptr(contr)), "bpe_gpt4_tables")
+            self._gpt4_ready = True
+
+    def split_gpt4(self, data):
+        """Chunk start offsets (uint64) of utf-8 `data` under GPT4_SPLIT_PATTERN, computed on the GPU."""
+        self._ensure_gpt4_tables()
+        b = np.frombuffer(data, dtype=np.uint8) if not isinstance(data, np.ndarray) else np.ascontiguousarray(data, dtype=np.uint8)
+        out = np.empty(max(b.size, 1), dtype=np.uint64)
+        n = ctypes.c_uint64()
+        self._check(self._lib.bpe_split_gpt4(self._h, _ptr(b) if b.size else None, b.size, _ptr(out), out.size, ctypes.byref(n)),
+                    "bpe_split_gpt4")
+        return out[: n.value].copy()
+
+    def load_text_gpt4(self, data, count_chunks=False):
+        """Upload utf-8 `data`, split it with GPT4_SPLIT_PATTERN on the GPU and make it the current stream."""
+        self._ensure_gpt4_tables()
+        b = np.frombuffer(data, dtype=np.uint8) if not isinstance(data, np.ndarray) else np.ascontiguousarray(data, dtype=np.uint8)
+        n = ctypes.c_uint64()
+        self._check(self._lib.bpe_load_text_gpt4(self._h, _ptr(b) if b.size else None, b.size,
+                                                 ctypes.byref(n) if count_chunks else None), "bpe_load_text_gpt4")
+        return n.value if count_chunks else None
 
     # ---- step-wise training (sharded loop; device pointers, e.g. torch tensors' data_ptr()) ----
     def set_stream(self, cuda_stream_ptr):

@@ -116,12 +116,15 @@ class Tokenizer:
             m[r, 0], m[r, 1] = pair
         return m
 
-    def _run_training(self, data, offsets, vocab_size, verbose):
+    def _run_training(self, data, offsets, vocab_size, verbose, device_split=False):
         """Shared by Basic/Regex: basic.py:21-49 / regex.py:37-70 minus the Python loops."""
         assert vocab_size >= 256
         num_merges = vocab_size - 256
         eng = self.engine
-        eng.load_stream(data, offsets)
+        if device_split:
+            eng.load_text_gpt4(data)      # regex.py:41-44 on the GPU (k_split.cuh)
+        else:
+            eng.load_stream(data, offsets)
         pairs, counts, done = eng.train(num_merges)
         self.last_timing = eng.timing()
         merges = {}
@@ -246,8 +249,19 @@ class RegexTokenizer(Tokenizer):
         self.special_tokens = {}
         self.inverse_special_tokens = {}
 
+    # texts at least this long are split on the GPU when the pattern is the GPT-4 one (same chunks as
+    # regex.findall — tests/test_split_rules.py, tests/test_gpu_split.py); short ones stay on the host
+    DEVICE_SPLIT_MIN_BYTES = 1 << 16
+
+    def _device_split(self, nbytes):
+        return self.pattern == GPT4_SPLIT_PATTERN and nbytes >= self.DEVICE_SPLIT_MIN_BYTES
+
     def train(self, text, vocab_size, verbose=False):
         assert vocab_size >= 256
+        data = text.encode("utf-8")
+        if self._device_split(len(data)):
+            self._run_training(data, None, vocab_size, verbose, device_split=True)
+            return
         data, offsets = split_text(self.compiled_pattern, text)
         self._run_training(data, offsets, vocab_size, verbose)
 
@@ -274,6 +288,9 @@ class RegexTokenizer(Tokenizer):
 
     def encode_ordinary(self, text):
         """regex.py:111-121."""
+        raw = text.encode("utf-8")
+        if self.merges and self._device_split(len(raw)):
+            return self.engine.encode(raw, self.engine.split_gpt4(raw), self._merge_array()).tolist()
         data, offsets = split_text(self.compiled_pattern, text)
         if not self.merges or len(data) < 2:
             return list(data)

@@ -1,0 +1,50 @@
+"""CPU: the data-parallel restatement of the GPT-4 split pattern (oracle/split_rules.py) against the
+installed `regex` module — the pattern minbpe uses at regex.py:19,41,114 — on the reference corpus,
+the synthetic corpus, hand-written edge cases and random strings over an adversarial alphabet."""
+import random
+
+import regex
+
+from oracle.split_rules import split
+
+GPT4 = regex.compile(
+    r"""'(?i:[sdmt]|ll|ve|re)|[^\r\n\p{L}\p{N}]?+\p{L}+|\p{N}{1,3}| ?[^\s\p{L}\p{N}]++[\r\n]*|\s*[\r\n]|\s+(?!\S)|\s+""")
+
+CASES = [
+    "", "a", " ", "  ", "\n", " \n ", "hello world", "  hello   world  ", "it's we'll I'VE you'Re 'tis 'sfoo x'llama",
+    " 's 'll", "a 'll b", "!!!word !word ! word", "\t!x", " !word", "12345 1 12 123 1234567", "a1b22c333d4444",
+    "x\n\n\ny", "!\n\n  x", "a \n b", "a  \n  \n  b", "\r\n\r\n a\r\nb \r\n", "a b c", "tab\t\tend\t", "''''a", "'s", "''s", "a''s",
+    "日本語 テキスト ١٢٣٤ ½⅓", "é'S ʼs", "don't.stop!!!\n\nnow", " 　x", "x 　", "\n x", "\n  x", "!\nx", "! \nx", "!' s",
+    "a'ſ b'K", "...'ll", "-'ll", "1's 22'll",
+]
+
+
+def check(text):
+    want = GPT4.findall(text)
+    got = split(text)
+    assert got == want, (text, got, want)
+
+
+def test_cases():
+    for t in CASES:
+        check(t)
+
+
+def test_corpora(taylorswift):
+    check(taylorswift)
+    from minbpe_b200.synth import generate
+    check(generate(1337, 1 << 20).tobytes().decode("utf-8"))
+
+
+def test_random_adversarial():
+    rnd = random.Random(12345)
+    alphabet = list("ab'sSdDmMtTlLvVeErR 12\t\n\r!.,' 　é日ſ½") + ["  ", "\n\n", "'ll", "'ve", " '"]
+    for _ in range(6000):
+        n = rnd.randint(0, 24)
+        check("".join(rnd.choice(alphabet) for _ in range(n)))
+    # random code points from several planes
+    pools = [range(0x20, 0x7f), range(0xa0, 0x250), range(0x370, 0x400), range(0x2000, 0x2070), range(0x3000, 0x3100),
+             range(0x1f600, 0x1f650), [0x9, 0xa, 0xd, 0x20, 0x85, 0x1680, 0x2028, 0x2029, 0x202f, 0x205f]]
+    for _ in range(2000):
+        n = rnd.randint(0, 30)
+        check("".join(chr(rnd.choice(rnd.choice(pools))) for _ in range(n)))
