@@ -326,6 +326,17 @@ def run_extras(args):
     hist_ms = (tr["loop_ms"] - tr["merge_kernel_ms"]) / max(rd, 1)
     out["rescan_256MiB"] = {"merges": int(rd), "loop_ms_per_merge": tr["loop_ms"] / max(rd, 1), "merge_ms": tr["merge_kernel_ms"] / max(rd, 1),
                             "hist_argmax_ms": hist_ms, "hist_GBps": 4.0 * tr["tokens_in"] / max(rd, 1) / (hist_ms / 1e3) / 1e9}
+    # device-side GPT-4 splitter: text bytes in, chunk offsets / marked stream out
+    eng.split_gpt4(raw[: 16 << 20])  # warm-up (tables, allocations)
+    eng.set_option(E.OPT_KERNEL_TIMING, 1)
+    t0 = time.perf_counter(); got = eng.split_gpt4(raw); dt = time.perf_counter() - t0
+    k_ms = eng.timing()["init_ms"]
+    t0 = time.perf_counter(); eng.load_text_gpt4(raw); torch.cuda.synchronize(); dl = time.perf_counter() - t0
+    eng.set_option(E.OPT_KERNEL_TIMING, 0)
+    t0 = time.perf_counter(); eng.load_stream(raw, offs); torch.cuda.synchronize(); dh = time.perf_counter() - t0
+    out["split_gpt4"] = {"bytes": size, "chunks": int(got.size), "equal_host_regex": bool(np.array_equal(got, offs)),
+                         "offsets_wall_s": dt, "kernels_ms": k_ms, "kernels_GBps_text": size / (k_ms / 1e3) / 1e9,
+                         "load_text_wall_s": dl, "load_stream_from_host_offsets_wall_s": dh}
     eng.load_stream(raw[: 64 << 20], offs[: int(np.searchsorted(offs, 64 << 20))])
     merges, _, done = eng.train(2048)
     torch.cuda.synchronize()

@@ -164,7 +164,9 @@ int bpe_step_result(bpe_handle *h, int32_t *out_pairs, int64_t *out_counts, int3
 
 typedef struct {
     double loop_ms;          /* device time of the last bpe_train merge loop (CUDA events) */
-    double init_ms;          /* device time of the initial histogram + table build */
+    double init_ms;          /* device time of the initial histogram + table build (bpe_train); of the
+                                split kernels after bpe_split_gpt4 / bpe_load_text_gpt4 with
+                                BPE_OPT_KERNEL_TIMING */
     double merge_kernel_ms;  /* summed device time of the fused merge kernel launches when
                                 per-kernel timing is on (BPE_OPT_KERNEL_TIMING), else 0 */
     uint64_t tokens_in;      /* sum over iterations of the stream length before the merge */

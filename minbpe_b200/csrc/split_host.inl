@@ -36,12 +36,19 @@ static int split_flags(bpe_handle *h, const unsigned char *d_bytes, u64 n, Split
     SP_CU(cudaMalloc(&W.re, n * 4)); SP_CU(cudaMalloc(&W.nnl, n * 4));
     SP_CU(cudaMalloc(&W.fpart, (size_t)ntiles * sizeof(Fwd))); SP_CU(cudaMalloc(&W.bpart, (size_t)ntiles * sizeof(Bwd)));
     const int g = h->sms * 8;
+    cudaEvent_t e0 = nullptr, e1 = nullptr;
+    if (h->opt_kernel_timing) { cudaEventCreate(&e0); cudaEventCreate(&e1); cudaEventRecord(e0, h->stream); }
     k_split_classify<<<g, 256, 0, h->stream>>>(d_bytes, n, h->d_cls, W.meta);
     k_split_reduce<<<ntiles, SP_THREADS, 0, h->stream>>>(W.meta, n, W.fpart, W.bpart);
     k_split_scan_parts<<<1, 1024, 0, h->stream>>>(W.fpart, W.bpart, ntiles);
     k_split_down<<<ntiles, SP_THREADS, 0, h->stream>>>(W.meta, n, W.fpart, W.bpart, W.rs, W.nl, W.cnt, W.re, W.nnl);
     k_split_rules<<<g, 256, 0, h->stream>>>(d_bytes, n, W.meta, h->d_contr, W.rs, W.nl, W.cnt, W.re, W.nnl, W.flag);
     h->tm.kernel_launches += 5;
+    if (e0) {   // BPE_OPT_KERNEL_TIMING: device time of the five split kernels -> bpe_timing.init_ms
+        cudaEventRecord(e1, h->stream); cudaEventSynchronize(e1);
+        float ms = 0; cudaEventElapsedTime(&ms, e0, e1); h->tm.init_ms = ms;
+        cudaEventDestroy(e0); cudaEventDestroy(e1);
+    }
     SP_CU(cudaGetLastError());
 #undef SP_CU
     return BPE_OK;
