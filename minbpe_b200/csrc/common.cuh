@@ -98,12 +98,13 @@ struct Ctl {
 // ---- segmented stream ------------------------------------------------------------------------
 // The stream lives in fixed segments of SEG_TOKENS words: segment t owns words
 // [t*SEG_TOKENS, (t+1)*SEG_TOKENS) and holds `count` tokens at its start.  A merge compacts
-// every segment in place, so no cross-segment prefix sum (and no serial dependency between CTAs)
-// is needed; the stream order is (segment, offset).  Edge records let a CTA see the tokens next
-// to its segment without touching the neighbour's body while that body is being rewritten; they
-// are double-buffered by merge parity.
-#define SEG_TOKENS 4096
-#define SEG_SHIFT 12
+// every segment in place, so no cross-segment prefix sum (and no serial dependency between warps)
+// is needed; the stream order is (segment, offset).  One segment = the 512 tokens one warp keeps
+// in registers (16 per lane), so the merge pass needs no block-level synchronisation at all.
+// Edge records let a warp see the tokens next to its segment without touching the neighbour's
+// body while that body is being rewritten; they are double-buffered by merge parity.
+#define SEG_TOKENS 512
+#define SEG_SHIFT 9
 struct __align__(32) Edge {
     u32 f[3];    // first three tokens (TOK_SENTINEL where the segment is shorter)
     u32 l[2];    // last two tokens: l[1] = last, l[0] = the one before it

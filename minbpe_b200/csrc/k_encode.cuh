@@ -177,44 +177,38 @@ __global__ void __launch_bounds__(256) k_encode_long(const unsigned char *__rest
     }
 }
 
-// Squeeze ENC_HOLE words out of every 4096-word segment, in place, and record the segment's edge
-// (count + boundary tokens) so that the stream machinery (pack, read-back) can take over.
+// Squeeze ENC_HOLE words out of every segment, in place, and record the segment's edge (count +
+// boundary tokens) so that the stream machinery (pack, read-back) can take over.  One warp per
+// segment; a lane owns 16 consecutive words (SEG_TOKENS = 32 x 16).
 __global__ void __launch_bounds__(256) k_compact_holes(u32 *__restrict__ w, u64 n, Edge *e0) {
-    __shared__ u32 s_tok[SEG_TOKENS];
-    __shared__ u32 s_scan[256];
-    const u32 tid = threadIdx.x;
+    static_assert(SEG_TOKENS == 512, "k_compact_holes: one lane owns 16 words");
+    const u32 lane = threadIdx.x & 31, wpb = blockDim.x >> 5;
     const u32 nseg = (u32)((n + SEG_TOKENS - 1) / SEG_TOKENS);
-    for (u32 t = blockIdx.x; t < nseg; t += gridDim.x) {
+    for (u32 t = blockIdx.x * wpb + (threadIdx.x >> 5); t < nseg; t += gridDim.x * wpb) {
         const u64 base = (u64)t * SEG_TOKENS;
         const u32 cnt = (u32)((n - base < SEG_TOKENS) ? (n - base) : SEG_TOKENS);
-        // thread owns 16 consecutive words
         u32 v[16], kept = 0;
 #pragma unroll
         for (int k = 0; k < 16; ++k) {
-            const u32 i = tid * 16 + k;
+            const u32 i = lane * 16 + k;
             v[k] = (i < cnt) ? w[base + i] : ENC_HOLE;
             kept += (v[k] != ENC_HOLE);
         }
-        s_scan[tid] = kept;
-        __syncthreads();
-        for (int o = 1; o < 256; o <<= 1) {
-            const u32 x = (tid >= (u32)o) ? s_scan[tid - o] : 0;
-            __syncthreads();
-            s_scan[tid] += x;
-            __syncthreads();
-        }
-        u32 dst = s_scan[tid] - kept;
-        const u32 total = s_scan[255];
+        u32 incl = kept;
 #pragma unroll
-        for (int k = 0; k < 16; ++k) if (v[k] != ENC_HOLE) s_tok[dst++] = v[k];
-        __syncthreads();
-        for (u32 i = tid; i < total; i += 256) w[base + i] = s_tok[i];
-        if (tid == 0) {
+        for (int o = 1; o < 32; o <<= 1) { const u32 x = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= (u32)o) incl += x; }
+        const u32 total = __shfl_sync(0xffffffffu, incl, 31);
+        u32 dst = incl - kept;
+        __syncwarp();   // every lane holds its words before anyone overwrites them
+#pragma unroll
+        for (int k = 0; k < 16; ++k) if (v[k] != ENC_HOLE) w[base + dst++] = v[k];
+        __syncwarp();
+        if (lane == 0) {
             Edge ed;
-            edge_from_tokens(ed, s_tok, total);
+            edge_from_tokens(ed, w + base, total);
             e0[t] = ed;
         }
-        __syncthreads();
+        __syncwarp();
     }
 }
 

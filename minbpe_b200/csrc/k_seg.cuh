@@ -70,27 +70,34 @@ __device__ __forceinline__ bool pack_wanted(const Ctl *ctl, int force) {
     return !ctl->done && !ctl->overflow && ctl->iter < ctl->max_iter && ctl->a == ctl->b;
 }
 
-// exclusive prefix sum of the segment counts (one block; 1024 threads x contiguous slices)
+// exclusive prefix sum of the segment counts (one block of 32 warps; every warp owns a contiguous
+// slice and walks it 32 records at a time, so the strided 32-byte records are fetched in parallel)
 __global__ void __launch_bounds__(1024) k_scan_counts(const Ctl *ctl, const Edge *e0, const Edge *e1,
                                                       u64 *__restrict__ offs, int force) {
     if (!pack_wanted(ctl, force)) return;
     const Edge *e = edges_cur(ctl, e0, e1);
     const u32 nseg = ctl->nseg;
-    const u32 per = (nseg + 1023) / 1024;
-    const u32 lo = threadIdx.x * per, hi = min(nseg, lo + per);
+    const u32 warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const u32 per = ((nseg + 31) / 32 + 31) & ~31u;          // slice per warp, a multiple of 32
+    const u32 lo = min(nseg, warp * per), hi = min(nseg, lo + per);
     u64 sum = 0;
-    for (u32 t = lo; t < hi; ++t) sum += e[t].count;
-    __shared__ u64 s[1024];
-    s[threadIdx.x] = sum;
+    for (u32 t = lo + lane; t < hi; t += 32) sum += e[t].count;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
+    __shared__ u64 s_w[32];
+    if (lane == 0) s_w[warp] = sum;
     __syncthreads();
-    for (int o = 1; o < 1024; o <<= 1) {  // Hillis-Steele inclusive scan
-        const u64 v = (threadIdx.x >= (u32)o) ? s[threadIdx.x - o] : 0;
-        __syncthreads();
-        s[threadIdx.x] += v;
-        __syncthreads();
+    u64 run = 0;
+    for (u32 k = 0; k < warp; ++k) run += s_w[k];
+    for (u32 t0 = lo; t0 < hi; t0 += 32) {
+        const u32 t = t0 + lane;
+        const u32 c = (t < hi) ? e[t].count : 0u;
+        u32 incl = c;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) { const u32 v = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= (u32)o) incl += v; }
+        if (t < hi) offs[t] = run + (incl - c);
+        run += __shfl_sync(0xffffffffu, incl, 31);
     }
-    u64 run = s[threadIdx.x] - sum;
-    for (u32 t = lo; t < hi; ++t) { offs[t] = run; run += e[t].count; }
 }
 
 // Pack the segmented stream into `dst` (contiguous).  flip=1: dst is the other ping-pong buffer
@@ -102,11 +109,12 @@ __global__ void __launch_bounds__(256) k_gather(Ctl *ctl, u32 *buf0, u32 *buf1, 
     const u32 *__restrict__ w = ctl->cur ? buf1 : buf0;
     u32 *__restrict__ dst = flip ? (ctl->cur ? buf0 : buf1) : dst_arg;
     const u32 nseg = ctl->nseg;
-    for (u32 t = blockIdx.x; t < nseg; t += gridDim.x) {
+    const u32 wpb = blockDim.x >> 5;
+    for (u32 t = blockIdx.x * wpb + (threadIdx.x >> 5); t < nseg; t += gridDim.x * wpb) {   // one warp per segment
         const u32 c = e[t].count;
         const u32 *__restrict__ src = w + (u64)t * SEG_TOKENS;
         u32 *__restrict__ d = dst + offs[t];
-        for (u32 i = threadIdx.x; i < c; i += blockDim.x) d[i] = src[i];
+        for (u32 i = threadIdx.x & 31; i < c; i += 32) d[i] = src[i];
     }
     if (!flip) return;
     __shared__ bool last;

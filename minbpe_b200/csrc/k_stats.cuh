@@ -6,8 +6,8 @@
 #include "k_seg.cuh"
 
 // =============================================================================================
-// Full histograms.  Both walk the segmented stream: one block per segment (grid-stride), four
-// tokens per thread per step (16-byte loads; segment bases are 16 KB aligned), equal keys inside
+// Full histograms.  Both walk the segmented stream: one warp per segment (grid-stride), four
+// tokens per thread per step (16-byte loads; segment bases are 2 KB aligned), equal keys inside
 // a warp are folded by __match_any_sync before the global reduction.  Stream position of token i
 // of segment t is t*SEG_TOKENS + i (monotone in stream order, used for first-occurrence order).
 // The pair (last token of t, first token of the next non-empty segment) belongs to segment t.
@@ -54,10 +54,11 @@ __global__ void __launch_bounds__(256) k_hist_dense(const u32 *__restrict__ buf0
     const u32 *__restrict__ w = ctl->cur ? buf1 : buf0;
     const Edge *e = edges_cur(ctl, e0, e1);
     const u32 nseg = ctl->nseg;
-    for (u32 t = blockIdx.x; t < nseg; t += gridDim.x) {
+    const u32 wpb = blockDim.x >> 5;
+    for (u32 t = blockIdx.x * wpb + (threadIdx.x >> 5); t < nseg; t += gridDim.x * wpb) {
         const u32 count = e[t].count;
         const u32 *__restrict__ seg = w + (u64)t * SEG_TOKENS;
-        for (u32 i0 = threadIdx.x * 4; i0 < count; i0 += blockDim.x * 4) {
+        for (u32 i0 = lane_id() * 4; i0 < count; i0 += 128) {
             const SegTokens r = seg_load4(seg, count, i0, e, t, nseg);
 #pragma unroll
             for (int k = 0; k < 4; ++k) {
@@ -126,10 +127,11 @@ __global__ void __launch_bounds__(256) k_hist_hash(const u32 *__restrict__ buf0,
     const u32 *__restrict__ w = ctl->cur ? buf1 : buf0;
     const Edge *e = edges_cur(ctl, e0, e1);
     const u32 nseg = ctl->nseg;
-    for (u32 t = blockIdx.x; t < nseg; t += gridDim.x) {
+    const u32 wpb = blockDim.x >> 5;
+    for (u32 t = blockIdx.x * wpb + (threadIdx.x >> 5); t < nseg; t += gridDim.x * wpb) {
         const u32 count = e[t].count;
         const u32 *__restrict__ seg = w + (u64)t * SEG_TOKENS;
-        for (u32 i0 = threadIdx.x * 4; i0 < count; i0 += blockDim.x * 4) {
+        for (u32 i0 = lane_id() * 4; i0 < count; i0 += 128) {
             const SegTokens r = seg_load4(seg, count, i0, e, t, nseg);
 #pragma unroll
             for (int k = 0; k < 4; ++k) {
@@ -255,6 +257,7 @@ __global__ void __launch_bounds__(256) k_argmax(Table t, Ctl *ctl, Best *partial
 // hit (later tiles exit as soon as they see found_pos in front of them).  Expected cost is
 // n / (tied * count) tokens — a tiny prefix unless counts are ~1.
 // =============================================================================================
+#define FF_GROUP 8
 __global__ void __launch_bounds__(256) k_find_first(const u32 *__restrict__ buf0, const u32 *__restrict__ buf1,
                                                     const Edge *e0, const Edge *e1, Table t, Ctl *ctl,
                                                     int *log_pairs, long long *log_counts, int sharded) {
@@ -265,19 +268,22 @@ __global__ void __launch_bounds__(256) k_find_first(const u32 *__restrict__ buf0
     const u64 best = ctl->best_count;
     __shared__ bool last;
     __shared__ u64 s_found;
-    for (u32 sg = blockIdx.x;; sg += gridDim.x) {   // segments in stream order
-        const u64 base = (u64)sg * SEG_TOKENS;
+    for (u32 g = blockIdx.x;; g += gridDim.x) {   // groups of FF_GROUP segments, in stream order
+        const u32 sg0 = g * FF_GROUP;
+        const u64 base = (u64)sg0 * SEG_TOKENS;
         if (threadIdx.x == 0) s_found = ld_volatile_u64(&ctl->found_pos);
         __syncthreads();
-        if (sg >= nseg || s_found < base) break;  // block-uniform: a hit in front of this segment ends the scan
-        const u32 count = e[sg].count;
-        const u32 *seg = w + base;
+        if (sg0 >= nseg || s_found < base) break;  // block-uniform: a hit in front of this group ends the scan
         u64 hit = POS_NONE;
-        for (u32 i = threadIdx.x; i < count; i += blockDim.x) {
-            const u32 right = (i + 1 < count) ? seg[i + 1] : seg_next_first(e, sg, nseg);
+        for (u32 i = threadIdx.x; i < FF_GROUP * SEG_TOKENS; i += blockDim.x) {   // ascending stream position
+            const u32 sg = sg0 + (i >> SEG_SHIFT), off = i & (SEG_TOKENS - 1);
+            if (sg >= nseg) break;
+            const u32 count = e[sg].count;
+            if (off >= count) continue;
+            const u32 right = (off + 1 < count) ? w[base + i + 1] : seg_next_first(e, sg, nseg);
             if (!(right & TOK_FLAG)) {
-                const u64 slot = table_find(t, pack_pair(seg[i] & TOK_MASK, right));
-                if (slot != POS_NONE && t.counts[slot] == best) { hit = base + i; break; }  // ascending i: this thread's first hit
+                const u64 slot = table_find(t, pack_pair(w[base + i] & TOK_MASK, right));
+                if (slot != POS_NONE && t.counts[slot] == best) { hit = base + i; break; }  // this thread's first hit
             }
         }
         if (hit != POS_NONE) atomicMin((ull *)&ctl->found_pos, (ull)hit);
