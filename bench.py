@@ -238,7 +238,9 @@ def run_ours(args):
 
     # ---- e2e: C-ABI calls from host buffers (upload + device split + W+K merges + merges back) ----
     pinned = pin_host(raw)
-    eng.split_gpt4(raw[: 1 << 20])   # class tables on the device, outside the timed region (once per handle)
+    # untimed warm-up of the same calls (class tables, first-touch of the big device allocations, clocks)
+    eng.load_text_gpt4(raw)
+    eng.train(W)
     torch.cuda.synchronize()
     t0 = time.perf_counter()
     eng.load_text_gpt4(raw)

@@ -177,3 +177,49 @@ __device__ __forceinline__ void bulk_g2s(void *dst_smem, const void *src_gmem, u
     asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
                  ::"r"(smem_addr(dst_smem)), "l"(src_gmem), "r"(bytes), "r"(smem_addr(bar)) : "memory");
 }
+
+// ---- the same with 32-bit shared-window addresses kept in registers.  Generic pointers into dynamic
+//      shared memory make the compiler rebuild the window base (S2R SR_CgaCtaId + LEA) and the index
+//      arithmetic in front of every access; the merge kernel's inner loop addresses shared memory
+//      explicitly instead. ----
+__device__ __forceinline__ u32 lds32(u32 addr) {
+    u32 v;
+    asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(addr) : "memory");
+    return v;
+}
+template <int OFF>
+__device__ __forceinline__ u32 lds32o(u32 addr) {
+    u32 v;
+    asm volatile("ld.shared.u32 %0, [%1+%2];" : "=r"(v) : "r"(addr), "n"(OFF) : "memory");
+    return v;
+}
+template <int OFF>
+__device__ __forceinline__ uint4 lds128o(u32 addr) {
+    uint4 v;
+    asm volatile("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4+%5];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(addr), "n"(OFF) : "memory");
+    return v;
+}
+__device__ __forceinline__ void sts32(u32 addr, u32 v) { asm volatile("st.shared.u32 [%0], %1;" ::"r"(addr), "r"(v) : "memory"); }
+template <int OFF>
+__device__ __forceinline__ void sts32o(u32 addr, u32 v) { asm volatile("st.shared.u32 [%0+%1], %2;" ::"r"(addr), "n"(OFF), "r"(v) : "memory"); }
+__device__ __forceinline__ void sts128(u32 addr, u32 x, u32 y, u32 z, u32 w) {
+    asm volatile("st.shared.v4.u32 [%0], {%1,%2,%3,%4};" ::"r"(addr), "r"(x), "r"(y), "r"(z), "r"(w) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_expect_tx_a(u32 bar_a, u32 tx_bytes) {
+    u64 state;
+    asm volatile("mbarrier.arrive.expect_tx.release.cta.shared::cta.b64 %0, [%1], %2;" : "=l"(state) : "r"(bar_a), "r"(tx_bytes) : "memory");
+    (void)state;
+}
+__device__ __forceinline__ void mbar_wait_a(u32 bar_a, u32 parity) {
+    u32 ok;
+    do {
+        asm volatile("{\n\t.reg .pred P;\n\t"
+                     "mbarrier.try_wait.parity.shared::cta.b64 P, [%1], %2, %3;\n\t"
+                     "selp.b32 %0, 1, 0, P;\n\t}"
+                     : "=r"(ok) : "r"(bar_a), "r"(parity), "r"(20000u) : "memory");
+    } while (!ok);
+}
+__device__ __forceinline__ void bulk_g2s_a(u32 dst_a, const void *src_gmem, u32 bytes, u32 bar_a) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(dst_a), "l"(src_gmem), "r"(bytes), "r"(bar_a) : "memory");
+}

@@ -61,12 +61,12 @@ __device__ __noinline__ void delta_cache_add(u32 *s_dkey, u32 *s_dcnt, ull *delt
     atomicAdd(&delta[idx], 1ull);   // cache neighbourhood full
 }
 
-// statistics delta of the merge that starts at token i of the segment (rules: k_merge.cuh).
-// s[-2..-1] and s[count..count+2] hold the neighbouring segments' tokens (or the sentinel).
-__device__ __noinline__ void delta_one(const u32 *s, int i, u32 a, u32 b, u32 V, u32 *s_dkey, u32 *s_dcnt, ull *delta) {
-    const u32 t0 = s[i], tm1 = s[i - 1], tm2 = s[i - 2], tp2 = s[i + 2], tp3 = s[i + 3];
-    const bool m_m2 = (((tm2 ^ a) & TOK_MASK) == 0) && tm1 == b;   // a merge starts at i-2
-    const bool m_p2 = (((tp2 ^ a) & TOK_MASK) == 0) && tp3 == b;   // a merge starts at i+2
+// statistics delta of the merge that starts at the token at shared address `at` (rules: k_merge.cuh).
+// The words at s[-2..-1] and s[count..count+2] hold the neighbouring segments' tokens (or the sentinel).
+__device__ __noinline__ void delta_one(u32 at, u32 a, u32 b, u32 V, u32 *s_dkey, u32 *s_dcnt, ull *delta) {
+    const u32 t0 = lds32(at), tm1 = lds32o<-4>(at), tm2 = lds32o<-8>(at), tp2 = lds32o<8>(at), tp3 = lds32o<12>(at);
+    const bool m_m2 = (((tm2 ^ a) & TOK_MASK) == 0) && tm1 == b;   // a merge starts two tokens earlier
+    const bool m_p2 = (((tp2 ^ a) & TOK_MASK) == 0) && tp3 == b;   // a merge starts two tokens later
     if (tm1 != TOK_SENTINEL && !(t0 & TOK_FLAG) && !m_m2) delta_cache_add(s_dkey, s_dcnt, delta, tm1 & TOK_MASK);
     if (!(tp2 & TOK_FLAG))   // also false for the sentinel (end of stream)
         delta_cache_add(s_dkey, s_dcnt, delta, m_p2 ? 2u * V : V + tp2);
@@ -80,6 +80,54 @@ struct SegArgs {
     u32 V;
     int force;
 };
+
+// one row (128 tokens, 4 per lane): merge starts m, kept tokens, replaced tokens written back to t[]
+template <int R>
+__device__ __forceinline__ void mark_row(u32 la, u32 lane, u32 count, u32 a, u32 b, u32 z, u32 (&t)[4], u32 &mn, u32 &keep,
+                                         u32 &dirty) {
+    const uint4 q = lds128o<R * 512>(la);
+    const u32 nx = lds32o<R * 512 + 16>(la), pv = lds32o<R * 512 - 4>(la);
+    t[0] = q.x; t[1] = q.y; t[2] = q.z; t[3] = q.w;
+    u32 m = 0;
+    m |= (((t[0] ^ a) & TOK_MASK) == 0 && t[1] == b) ? 1u : 0u;
+    m |= (((t[1] ^ a) & TOK_MASK) == 0 && t[2] == b) ? 2u : 0u;
+    m |= (((t[2] ^ a) & TOK_MASK) == 0 && t[3] == b) ? 4u : 0u;
+    m |= (((t[3] ^ a) & TOK_MASK) == 0 && nx == b) ? 8u : 0u;
+    const u32 pm = (((pv ^ a) & TOK_MASK) == 0 && t[0] == b) ? 1u : 0u;
+    const u32 d = ((m << 1) | pm) & 0xfu;   // dropped: the token after a merge start
+    u32 valid = 0xfu;
+    if (R * 128u + 128u > count) {          // warp-uniform: the row that holds the end of the segment
+        const int rem = (int)count - (int)(R * 128 + lane * 4);
+        valid = rem >= 4 ? 0xfu : (rem <= 0 ? 0u : ((1u << rem) - 1u));
+    }
+    mn = m & valid;                         // a merge only starts at a token this segment owns
+    keep = ~d & valid;
+    dirty |= (mn | (keep ^ valid)) ? (1u << R) : 0u;
+    if (mn) {                               // few lanes: the merged token takes its place in the registers
+        if (mn & 1u) t[0] = z | (t[0] & TOK_FLAG);
+        if (mn & 2u) t[1] = z | (t[1] & TOK_FLAG);
+        if (mn & 4u) t[2] = z | (t[2] & TOK_FLAG);
+        if (mn & 8u) t[3] = z | (t[3] & TOK_FLAG);
+    }
+}
+
+// write the kept tokens of one row to their compacted place (word offset `off` of the stage)
+__device__ __forceinline__ void scatter_row(u32 s_a, u32 lane, u32 off, u32 row_kept, u32 lane_excl, u32 kp, const u32 (&t)[4]) {
+    if (row_kept == 128u) {                 // warp-uniform: nothing dropped in this row, it only moves
+        const u32 p = s_a + ((off + 4u * lane) << 2);
+        if ((off & 3u) == 0) sts128(p, t[0], t[1], t[2], t[3]);
+        else { sts32(p, t[0]); sts32o<4>(p, t[1]); sts32o<8>(p, t[2]); sts32o<12>(p, t[3]); }
+    } else {
+        u32 p = s_a + ((off + lane_excl) << 2);
+        if (kp & 1u) sts32(p, t[0]);
+        p += (kp << 2) & 4u;
+        if (kp & 2u) sts32(p, t[1]);
+        p += (kp << 1) & 4u;
+        if (kp & 4u) sts32(p, t[2]);
+        p += kp & 4u;
+        if (kp & 8u) sts32(p, t[3]);
+    }
+}
 
 __global__ void __launch_bounds__(MS_THREADS, MS_MINBLOCKS) k_merge_seg(SegArgs A) {
     Ctl *ctl = A.ctl;
@@ -102,13 +150,14 @@ __global__ void __launch_bounds__(MS_THREADS, MS_MINBLOCKS) k_merge_seg(SegArgs 
     const u32 a = (u32)ctl->a, b = (u32)ctl->b, z = (u32)ctl->z;
     const u32 nseg = ctl->nseg;
 
-    u32 *ws = s_warp + warp * MS_WARP_WORDS;        // [MS_STAGES][MS_SW] staging ring of this warp
-    u32 *wmeta = ws + MS_STAGES * MS_SW;            // [MS_STAGES][MS_META]
-    u32 *wbe = wmeta + MS_STAGES * MS_META;         // [MS_BE][8] edge records batch_seg-1 .. batch_seg+MS_BATCH
-    u64 *wbar = s_bar + warp * MS_STAGES;
+    // this warp's private shared memory, as 32-bit shared-window byte addresses
+    const u32 ws_a = smem_addr(s_warp + warp * MS_WARP_WORDS);   // [MS_STAGES][MS_SW] staging ring
+    const u32 wmeta_a = ws_a + MS_STAGES * MS_SW * 4;            // [MS_STAGES][MS_META]
+    const u32 wbe_a = wmeta_a + MS_STAGES * MS_META * 4;         // [MS_BE][8] edge records batch_seg-1 .. batch_seg+MS_BATCH
+    const u32 wbar_a = smem_addr(s_bar + warp * MS_STAGES);
 
     if (lane == 0) {
-        for (int s = 0; s < MS_STAGES; ++s) mbar_init(&wbar[s], 1);
+        for (int s = 0; s < MS_STAGES; ++s) mbar_init(s_bar + warp * MS_STAGES + s, 1);
         fence_mbar_init();
     }
     for (u32 i = tid; i < MS_DCACHE; i += MS_THREADS) { s_dkey[i] = 0xffffffffu; s_dcnt[i] = 0; }
@@ -117,14 +166,16 @@ __global__ void __launch_bounds__(MS_THREADS, MS_MINBLOCKS) k_merge_seg(SegArgs 
 
     // ---- issue side: next non-empty segment of this warp -> bulk copy into `stage` ----
     u32 batch_seg = 0, batch_pos = MS_BATCH;   // warp-uniform
-    // word of the batch's edge-record window (relative to record k) that lane l copies into meta[l]
-    const u32 meta_src = lane == 0 ? 4u : lane == 1 ? 3u : lane < 5 ? 14u + lane : lane < 8 ? 0u : lane < 16 ? lane : 0u;
+    // byte offset inside the batch's edge-record window (relative to record k) of the word lane l copies
+    // into meta[l]: meta[0..4] = P0 P1 N0 N1 N2 = previous record's l[1], l[0], next record's f[0..2];
+    // meta[8..15] = the segment's own record (for the untouched case); meta[5] = seg, meta[6] = count
+    const u32 meta_src = 4u * (lane == 0 ? 4u : lane == 1 ? 3u : lane < 5 ? 14u + lane : lane < 8 ? 0u : lane < 16 ? lane : 0u);
     bool exhausted = false;
     auto issue = [&](u32 stage) {
-        u32 *meta = wmeta + stage * MS_META;
+        const u32 meta_a = wmeta_a + stage * (MS_META * 4);
         for (;;) {
             if (exhausted) {
-                if (lane == 0) meta[5] = MS_INVALID;
+                if (lane == 0) sts32o<20>(meta_a, MS_INVALID);
                 __syncwarp();
                 return;
             }
@@ -144,44 +195,42 @@ __global__ void __launch_bounds__(MS_THREADS, MS_MINBLOCKS) k_merge_seg(SegArgs 
                         q0 = make_uint4(TOK_SENTINEL, TOK_SENTINEL, TOK_SENTINEL, TOK_SENTINEL);
                         q1 = make_uint4(TOK_SENTINEL, 3u, 0u, 0u);
                     }
-                    uint4 *d = reinterpret_cast<uint4 *>(wbe + lane * 8);
-                    d[0] = q0; d[1] = q1;
+                    sts128(wbe_a + lane * 32, q0.x, q0.y, q0.z, q0.w);
+                    sts128(wbe_a + lane * 32 + 16, q1.x, q1.y, q1.z, q1.w);
                 }
                 __syncwarp();
             }
             const u32 k = batch_pos++;
             const u32 seg = batch_seg + k;
             if (seg >= nseg) { exhausted = true; continue; }
-            const u32 *me = wbe + (k + 1) * 8;
-            const u32 cnt = me[5];
+            const u32 rec_a = wbe_a + k * 32;          // record k = the segment in front of this one
+            const u32 cnt = lds32o<32 + 20>(rec_a);
             if (cnt == 0) {   // empty segment: only its (empty) edge record is carried over
                 if (lane < 8) reinterpret_cast<u32 *>(&e_next[seg])[lane] = (lane < 5) ? TOK_SENTINEL : 0u;
                 continue;
             }
-            const u32 cm1 = wbe[k * 8 + 5], cp1 = wbe[(k + 2) * 8 + 5];
-            // meta[0..4] = P0 P1 N0 N1 N2 (previous record's l[1], l[0]; next record's f[0..2]), [5] = seg,
-            // [6] = count, [8..15] = the segment's own edge record (for the untouched case): one load per lane
-            u32 mv = wbe[k * 8 + meta_src];
+            const u32 cm1 = lds32o<20>(rec_a), cp1 = lds32o<64 + 20>(rec_a);
+            const u32 st_a = ws_a + stage * (MS_SW * 4);
+            u32 mv = lds32(rec_a + meta_src);
             if (lane == 5) mv = seg;
             if (lane == 6) mv = cnt;
-            if (lane < 16) meta[lane] = mv;
+            if (lane < 16) sts32(meta_a + lane * 4, mv);
+            if (lane < 2) sts32(st_a + (MS_PAD - 1 - lane) * 4, mv);   // s[-1] = P0, s[-2] = P1
             if (!(cm1 >= 2 && cp1 >= 3)) {   // short / empty neighbours: walk the edge records
                 __syncwarp();
                 if (lane == 0) {
                     u32 N[3], P[2];
                     seg_neighbours(e_cur, seg, nseg, N, P);
-                    meta[0] = P[0]; meta[1] = P[1]; meta[2] = N[0]; meta[3] = N[1]; meta[4] = N[2];
+                    sts32o<0>(meta_a, P[0]); sts32o<4>(meta_a, P[1]); sts32o<8>(meta_a, N[0]); sts32o<12>(meta_a, N[1]); sts32o<16>(meta_a, N[2]);
+                    sts32o<(MS_PAD - 1) * 4>(st_a, P[0]); sts32o<(MS_PAD - 2) * 4>(st_a, P[1]);
                 }
             }
             __syncwarp();
             if (lane == 0) {
-                u32 *st = ws + stage * MS_SW;
-                st[MS_PAD - 1] = meta[0];   // s[-1], s[-2]
-                st[MS_PAD - 2] = meta[1];
                 const u32 bytes = ((cnt + 3u) & ~3u) * 4u;
                 fence_proxy_async_smem();   // the stage was last written with ordinary stores (in-place compaction)
-                mbar_arrive_expect_tx(&wbar[stage], bytes);
-                bulk_g2s(st + MS_PAD, w + (u64)seg * SEG_TOKENS, bytes, &wbar[stage]);
+                mbar_arrive_expect_tx_a(wbar_a + stage * 8, bytes);
+                bulk_g2s_a(st_a + MS_PAD * 4, w + (u64)seg * SEG_TOKENS, bytes, wbar_a + stage * 8);
             }
             __syncwarp();
             return;
@@ -193,55 +242,27 @@ __global__ void __launch_bounds__(MS_THREADS, MS_MINBLOCKS) k_merge_seg(SegArgs 
     for (u32 j = 0;; ++j) {
         const u32 stage = j % MS_STAGES;
         issue((j + MS_STAGES - 1) % MS_STAGES);   // the stage consumed in the previous round
-        const u32 *meta = wmeta + stage * MS_META;
-        const u32 seg = meta[5];
+        const u32 meta_a = wmeta_a + stage * (MS_META * 4);
+        const u32 seg = lds32o<20>(meta_a);
         if (seg == MS_INVALID) break;
-        const u32 count = meta[6];
-        u32 *s = ws + stage * MS_SW + MS_PAD;     // s[i] = token i of the segment
-        mbar_wait(&wbar[stage], (j / MS_STAGES) & 1u);
-        if (lane < 3) s[count + lane] = meta[2 + lane];   // the three tokens that follow the segment
+        const u32 count = lds32o<24>(meta_a);
+        const u32 s_a = ws_a + stage * (MS_SW * 4) + MS_PAD * 4;   // address of token 0 of the segment
+        mbar_wait_a(wbar_a + stage * 8, (j / MS_STAGES) & 1u);
+        if (lane < 3) sts32(s_a + (count + lane) * 4, lds32(meta_a + 8 + lane * 4));   // the three tokens that follow
         __syncwarp();
 
         // ---- mark: row r = tokens [128r, 128r+128), four consecutive tokens per lane ----
-        u32 t[4][4], mn[4], keep[4];
+        u32 t[4][4], mn[4] = {0, 0, 0, 0}, keep[4] = {0, 0, 0, 0};
         u32 dirty = 0;
-#pragma unroll
-        for (int r = 0; r < 4; ++r) {
-            mn[r] = 0; keep[r] = 0;
-            if ((u32)r * 128u < count) {   // warp-uniform
-                const u32 li = r * 128 + lane * 4;
-                const uint4 q = *reinterpret_cast<const uint4 *>(s + li);
-                t[r][0] = q.x; t[r][1] = q.y; t[r][2] = q.z; t[r][3] = q.w;
-                const u32 nx = s[li + 4], pv = s[li - 1];
-                u32 m = 0;
-                m |= (((t[r][0] ^ a) & TOK_MASK) == 0 && t[r][1] == b) ? 1u : 0u;
-                m |= (((t[r][1] ^ a) & TOK_MASK) == 0 && t[r][2] == b) ? 2u : 0u;
-                m |= (((t[r][2] ^ a) & TOK_MASK) == 0 && t[r][3] == b) ? 4u : 0u;
-                m |= (((t[r][3] ^ a) & TOK_MASK) == 0 && nx == b) ? 8u : 0u;
-                const u32 pm = (((pv ^ a) & TOK_MASK) == 0 && t[r][0] == b) ? 1u : 0u;
-                const u32 d = ((m << 1) | pm) & 0xfu;   // dropped: the token after a merge start
-                u32 valid = 0xfu;
-                if ((u32)r * 128u + 128u > count) {     // warp-uniform: the row that holds the end of the segment
-                    const int rem = (int)count - (int)li;
-                    valid = rem >= 4 ? 0xfu : (rem <= 0 ? 0u : ((1u << rem) - 1u));
-                }
-                mn[r] = m & valid;                      // a merge only starts at a token this segment owns
-                keep[r] = ~d & valid;
-                dirty |= (mn[r] | (keep[r] ^ valid)) ? (1u << r) : 0u;
-                if (mn[r]) {                            // few lanes: the merged token takes its place in the registers
-                    if (mn[r] & 1u) t[r][0] = z | (t[r][0] & TOK_FLAG);
-                    if (mn[r] & 2u) t[r][1] = z | (t[r][1] & TOK_FLAG);
-                    if (mn[r] & 4u) t[r][2] = z | (t[r][2] & TOK_FLAG);
-                    if (mn[r] & 8u) t[r][3] = z | (t[r][3] & TOK_FLAG);
-                }
-            } else {
-                t[r][0] = t[r][1] = t[r][2] = t[r][3] = TOK_SENTINEL;
-            }
-        }
+        const u32 la = s_a + lane * 16;
+        mark_row<0>(la, lane, count, a, b, z, t[0], mn[0], keep[0], dirty);
+        if (count > 128u) mark_row<1>(la, lane, count, a, b, z, t[1], mn[1], keep[1], dirty);
+        if (count > 256u) mark_row<2>(la, lane, count, a, b, z, t[2], mn[2], keep[2], dirty);
+        if (count > 384u) mark_row<3>(la, lane, count, a, b, z, t[3], mn[3], keep[3], dirty);
         dirty = __reduce_or_sync(FULL, dirty);   // rows in which some token is replaced or dropped
         if (!dirty) {
             // untouched segment: nothing to write, the edge record carries over
-            if (lane < 8) reinterpret_cast<u32 *>(&e_next[seg])[lane] = meta[8 + lane];
+            if (lane < 8) reinterpret_cast<u32 *>(&e_next[seg])[lane] = lds32(meta_a + 32 + lane * 4);
             __syncwarp();
             continue;
         }
@@ -253,7 +274,7 @@ __global__ void __launch_bounds__(MS_THREADS, MS_MINBLOCKS) k_merge_seg(SegArgs 
             while (mall) {   // one pass per merge start of this lane
                 const int bit = __ffs(mall) - 1;
                 mall &= mall - 1;
-                delta_one(s, (bit >> 2) * 128 + (int)lane * 4 + (bit & 3), a, b, A.V, s_dkey, s_dcnt, A.delta);
+                delta_one(la + (bit >> 2) * 512 + (bit & 3) * 4, a, b, A.V, s_dkey, s_dcnt, A.delta);
             }
         }
 
@@ -267,49 +288,35 @@ __global__ void __launch_bounds__(MS_THREADS, MS_MINBLOCKS) k_merge_seg(SegArgs 
         }
         const u32 tot = __shfl_sync(FULL, incl, 31);
         const u32 excl = incl - own;
-        u32 rowoff[4];
-        rowoff[0] = 0;
-        rowoff[1] = tot & 0xffu;
-        rowoff[2] = rowoff[1] + ((tot >> 8) & 0xffu);
-        rowoff[3] = rowoff[2] + ((tot >> 16) & 0xffu);
-        const u32 new_count = rowoff[3] + (tot >> 24);
+        const u32 k0 = tot & 0xffu, k1 = (tot >> 8) & 0xffu, k2 = (tot >> 16) & 0xffu, k3 = tot >> 24;
+        const u32 off1 = k0, off2 = k0 + k1, off3 = off2 + k2;
+        const u32 new_count = off3 + k3;
         const int first_dirty = __ffs(dirty) - 1;   // rows in front of it stay where they are
         __syncwarp();                               // all lanes hold their tokens; delta reads are done
 
         // ---- compact in place inside the stage, from the first dirty row on ----
-#pragma unroll
-        for (int r = 0; r < 4; ++r) {
-            if (r >= first_dirty && (u32)r * 128u < count) {
-                const u32 kp = keep[r];
-                const u32 d0 = rowoff[r] + ((excl >> (8 * r)) & 0xffu);
-                const u32 d1 = d0 + (kp & 1u);
-                const u32 d2 = d1 + ((kp >> 1) & 1u);
-                const u32 d3 = d2 + ((kp >> 2) & 1u);
-                if (kp & 1u) s[d0] = t[r][0];
-                if (kp & 2u) s[d1] = t[r][1];
-                if (kp & 4u) s[d2] = t[r][2];
-                if (kp & 8u) s[d3] = t[r][3];
-            }
-        }
+        if (first_dirty <= 0) scatter_row(s_a, lane, 0u, k0, excl & 0xffu, keep[0], t[0]);
+        if (first_dirty <= 1 && count > 128u) scatter_row(s_a, lane, off1, k1, (excl >> 8) & 0xffu, keep[1], t[1]);
+        if (first_dirty <= 2 && count > 256u) scatter_row(s_a, lane, off2, k2, (excl >> 16) & 0xffu, keep[2], t[2]);
+        if (count > 384u) scatter_row(s_a, lane, off3, k3, excl >> 24, keep[3], t[3]);
         __syncwarp();
         // ---- copy-out: 16-byte vectors from the first dirty row to the new end (the up to three
         //      words past new_count land in the dead part of the segment) ----
         {
-            uint4 *__restrict__ gp = reinterpret_cast<uint4 *>(w + (u64)seg * SEG_TOKENS);
-            const uint4 *sp = reinterpret_cast<const uint4 *>(s);
+            uint4 *__restrict__ gp = reinterpret_cast<uint4 *>(w + (u64)seg * SEG_TOKENS) + lane;
             const u32 vend = (new_count + 3u) >> 2;
-#pragma unroll
-            for (int it = 0; it < 4; ++it) {
-                const u32 v = it * 32 + lane;
-                if (it >= first_dirty && v < vend) gp[v] = sp[v];
-            }
+            if (first_dirty <= 0 && lane < vend) gp[0] = lds128o<0>(la);
+            if (first_dirty <= 1 && lane + 32u < vend) gp[32] = lds128o<512>(la);
+            if (first_dirty <= 2 && lane + 64u < vend) gp[64] = lds128o<1024>(la);
+            if (lane + 96u < vend) gp[96] = lds128o<1536>(la);
         }
         // ---- the segment's new edge record ----
         {
             // lane:  0 1 2 -> f[0..2]   3 4 -> l[0], l[1] = tokens new_count-2, new_count-1   5 -> count   6 7 -> 0
             const u32 idx = lane < 3 ? lane : new_count + lane - 5u;
             const bool have = lane < 3 ? (lane < new_count) : (new_count + lane >= 5u);
-            u32 word = have ? s[idx & (SEG_TOKENS - 1)] : TOK_SENTINEL;
+            u32 word = TOK_SENTINEL;
+            if (have && lane < 5) word = lds32(s_a + (idx & (SEG_TOKENS - 1)) * 4);
             if (lane == 5) word = new_count;
             if (lane > 5) word = 0;
             if (lane < 8) reinterpret_cast<u32 *>(&e_next[seg])[lane] = word;   // Edge = f[3], l[2], count, pad[2]
