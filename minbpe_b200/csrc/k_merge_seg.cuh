@@ -18,7 +18,9 @@
 #include "k_merge.cuh"
 #include "k_seg.cuh"
 
+#ifndef MS_WARPS
 #define MS_WARPS 8
+#endif
 #define MS_THREADS (MS_WARPS * 32)
 #ifndef MS_STAGES
 #define MS_STAGES 2
@@ -29,7 +31,9 @@
 #ifndef MS_DCACHE_LOG2
 #define MS_DCACHE_LOG2 9
 #endif
+#ifndef MS_BATCH
 #define MS_BATCH 8                          // consecutive segments per ticket
+#endif
 #define MS_PAD 4                            // body starts at word 4 of a stage (16-byte aligned); s[-1], s[-2] = previous tokens
 #define MS_SW (SEG_TOKENS + 8)              // words per stage: pad, body, three following tokens
 #define MS_META 16                          // per stage: P0 P1 N0 N1 N2 seg count - | the segment's own edge record
