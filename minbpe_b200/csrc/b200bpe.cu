@@ -48,6 +48,7 @@ struct bpe_handle {
     int *log_pairs = nullptr; long long *log_counts = nullptr; int log_cap = 0;
     Best *partials = nullptr;
     unsigned char *d_cls = nullptr, *d_contr = nullptr;   // code-point class / contraction tables of the GPT-4 splitter
+    unsigned char *split_slab = nullptr; u64 split_cap = 0;   // working set of the splitter, kept between calls (split_host.inl)
     int argmax_grid = 0, merge_grid = 0, merge_grid_same = 0, merge_grid_seg = 0, ff_grid = 0;
 
     // options
@@ -182,6 +183,7 @@ extern "C" int bpe_destroy(bpe_handle *h) {
     if (h->partials) cudaFree(h->partials);
     if (h->d_cls) cudaFree(h->d_cls);
     if (h->d_contr) cudaFree(h->d_contr);
+    if (h->split_slab) cudaFree(h->split_slab);
     if (h->ctl) cudaFree(h->ctl);
     if (h->h_ctl) cudaFreeHost(h->h_ctl);
     if (h->own_stream) cudaStreamDestroy(h->own_stream);
@@ -216,6 +218,7 @@ static int ensure_stream_capacity(bpe_handle *h, u64 n) {
     // round up to whole tiles (+ slack) so 16-byte loads at the tail stay inside the allocation
     const u64 need = ((n + MG_TILE - 1) / MG_TILE + 1) * MG_TILE;
     if (need > h->cap_tokens) {
+        if (h->split_slab) { cudaFree(h->split_slab); h->split_slab = nullptr; h->split_cap = 0; }   // make room first
         for (int i = 0; i < 2; ++i) { if (h->buf[i]) cudaFree(h->buf[i]); h->buf[i] = nullptr; }
         h->cap_tokens = 0;
         for (int i = 0; i < 2; ++i) CU(cudaMalloc(&h->buf[i], need * 4));

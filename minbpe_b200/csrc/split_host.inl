@@ -13,44 +13,70 @@ extern "C" int bpe_gpt4_tables(bpe_handle *h, const uint8_t *cls_table, const ui
     return BPE_OK;
 }
 
+// Working set of one split call, carved out of a slab that stays with the handle (grow-only; given
+// back when the stream buffers have to grow, and in bpe_destroy): 23 bytes per text byte, so
+// allocating and freeing it on every call costs more than the kernels.
 struct SplitWork {
-    unsigned char *meta = nullptr, *flag = nullptr;
+    unsigned char *bytes = nullptr, *meta = nullptr, *flag = nullptr;
     u32 *rs = nullptr, *nl = nullptr, *cnt = nullptr, *re = nullptr, *nnl = nullptr;
     Fwd *fpart = nullptr; Bwd *bpart = nullptr;
-    void release() {
-        cudaFree(meta); cudaFree(flag); cudaFree(rs); cudaFree(nl); cudaFree(cnt); cudaFree(re); cudaFree(nnl);
-        cudaFree(fpart); cudaFree(bpart);
-        *this = SplitWork();
-    }
 };
 
-// d_bytes (device, n bytes of UTF-8) -> W.flag[i] = 1 at every chunk start.  Caller releases W.
-static int split_flags(bpe_handle *h, const unsigned char *d_bytes, u64 n, SplitWork &W) {
+static void split_slab_release(bpe_handle *h) {
+    if (h->split_slab) cudaFree(h->split_slab);
+    h->split_slab = nullptr; h->split_cap = 0;
+}
+
+static int split_carve(bpe_handle *h, u64 n, SplitWork &W) {
+    const u64 a = (n + 255) & ~255ull;
+    const u64 ntiles = (n + SP_TILE - 1) / SP_TILE;
+    const u64 parts = ((ntiles * sizeof(Fwd) + 255) & ~255ull) + ((ntiles * sizeof(Bwd) + 255) & ~255ull);
+    const u64 need = 3 * a + 5 * 4 * a + parts + 256;
+    if (need > h->split_cap) {
+        split_slab_release(h);
+        cudaError_t e = cudaMalloc(&h->split_slab, need);
+        if (e != cudaSuccess) return fail(h, BPE_ERR_CUDA, std::string("cudaMalloc(split working set): ") + cudaGetErrorString(e));
+        h->split_cap = need;
+    }
+    unsigned char *p = h->split_slab;
+    W.bytes = p; p += a;
+    W.meta = p; p += a;
+    W.flag = p; p += a;
+    W.rs = (u32 *)p; p += 4 * a;
+    W.nl = (u32 *)p; p += 4 * a;
+    W.cnt = (u32 *)p; p += 4 * a;
+    W.re = (u32 *)p; p += 4 * a;
+    W.nnl = (u32 *)p; p += 4 * a;
+    W.fpart = (Fwd *)p; p += (ntiles * sizeof(Fwd) + 255) & ~255ull;
+    W.bpart = (Bwd *)p;
+    return BPE_OK;
+}
+
+// host text (n bytes of UTF-8) -> W.bytes on the device and W.flag[i] = 1 at every chunk start
+static int split_flags(bpe_handle *h, const uint8_t *bytes, u64 n, SplitWork &W) {
     if (!h->d_cls) return fail(h, BPE_ERR_STATE, "call bpe_gpt4_tables first");
     if (n == 0) return BPE_OK;
     if (n >= 0xfffffff0ull) return fail(h, BPE_ERR_ARG, "device split handles at most 4 GiB - 16 per call");
+    int rc = split_carve(h, n, W);
+    if (rc) return rc;
+    CU(cudaMemcpyAsync(W.bytes, bytes, n, cudaMemcpyHostToDevice, h->stream));
+    h->tm.h2d_bytes = n;
     const u32 ntiles = (u32)((n + SP_TILE - 1) / SP_TILE);
-#define SP_CU(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) { W.release(); return fail(h, BPE_ERR_CUDA, std::string(#call) + ": " + cudaGetErrorString(e_)); } } while (0)
-    SP_CU(cudaMalloc(&W.meta, n)); SP_CU(cudaMalloc(&W.flag, n));
-    SP_CU(cudaMalloc(&W.rs, n * 4)); SP_CU(cudaMalloc(&W.nl, n * 4)); SP_CU(cudaMalloc(&W.cnt, n * 4));
-    SP_CU(cudaMalloc(&W.re, n * 4)); SP_CU(cudaMalloc(&W.nnl, n * 4));
-    SP_CU(cudaMalloc(&W.fpart, (size_t)ntiles * sizeof(Fwd))); SP_CU(cudaMalloc(&W.bpart, (size_t)ntiles * sizeof(Bwd)));
     const int g = h->sms * 8;
     cudaEvent_t e0 = nullptr, e1 = nullptr;
     if (h->opt_kernel_timing) { cudaEventCreate(&e0); cudaEventCreate(&e1); cudaEventRecord(e0, h->stream); }
-    k_split_classify<<<g, 256, 0, h->stream>>>(d_bytes, n, h->d_cls, W.meta);
+    k_split_classify<<<g, 256, 0, h->stream>>>(W.bytes, n, h->d_cls, W.meta);
     k_split_reduce<<<ntiles, SP_THREADS, 0, h->stream>>>(W.meta, n, W.fpart, W.bpart);
     k_split_scan_parts<<<1, 1024, 0, h->stream>>>(W.fpart, W.bpart, ntiles);
     k_split_down<<<ntiles, SP_THREADS, 0, h->stream>>>(W.meta, n, W.fpart, W.bpart, W.rs, W.nl, W.cnt, W.re, W.nnl);
-    k_split_rules<<<g, 256, 0, h->stream>>>(d_bytes, n, W.meta, h->d_contr, W.rs, W.nl, W.cnt, W.re, W.nnl, W.flag);
+    k_split_rules<<<g, 256, 0, h->stream>>>(W.bytes, n, W.meta, h->d_contr, W.rs, W.nl, W.cnt, W.re, W.nnl, W.flag);
     h->tm.kernel_launches += 5;
     if (e0) {   // BPE_OPT_KERNEL_TIMING: device time of the five split kernels -> bpe_timing.init_ms
         cudaEventRecord(e1, h->stream); cudaEventSynchronize(e1);
         float ms = 0; cudaEventElapsedTime(&ms, e0, e1); h->tm.init_ms = ms;
         cudaEventDestroy(e0); cudaEventDestroy(e1);
     }
-    SP_CU(cudaGetLastError());
-#undef SP_CU
+    CU(cudaGetLastError());
     return BPE_OK;
 }
 
@@ -83,27 +109,22 @@ extern "C" int bpe_split_gpt4(bpe_handle *h, const uint8_t *bytes, uint64_t n, u
     *n_chunks = 0;
     h->tm.h2d_bytes = 0; h->tm.d2h_bytes = 0; h->tm.kernel_launches = 0;
     if (n == 0) return BPE_OK;
-    unsigned char *d_bytes = nullptr;
-    CU(cudaMalloc(&d_bytes, n));
-    cudaError_t e = cudaMemcpyAsync(d_bytes, bytes, n, cudaMemcpyHostToDevice, h->stream);
-    if (e != cudaSuccess) { cudaFree(d_bytes); return fail(h, BPE_ERR_CUDA, cudaGetErrorString(e)); }
-    h->tm.h2d_bytes = n;
     SplitWork W;
-    int rc = split_flags(h, d_bytes, n, W);
+    int rc = split_flags(h, bytes, n, W);
     u64 *d_offs = nullptr;
     if (!rc && cudaMalloc(&d_offs, n * 8) != cudaSuccess) rc = fail(h, BPE_ERR_CUDA, "cudaMalloc offsets");
     if (!rc) rc = flags_to_offsets(h, W.flag, n, d_offs, n_chunks);
     if (!rc) {
         if (*n_chunks > cap) rc = fail(h, BPE_ERR_CAPACITY, "offsets buffer too small");
         else {
-            e = cudaMemcpyAsync(out_offsets, d_offs, *n_chunks * 8, cudaMemcpyDeviceToHost, h->stream);
+            cudaError_t e = cudaMemcpyAsync(out_offsets, d_offs, *n_chunks * 8, cudaMemcpyDeviceToHost, h->stream);
             if (e == cudaSuccess) e = cudaStreamSynchronize(h->stream);
             if (e != cudaSuccess) rc = fail(h, BPE_ERR_CUDA, cudaGetErrorString(e));
             h->tm.d2h_bytes = *n_chunks * 8;
         }
     }
     cudaStreamSynchronize(h->stream);
-    W.release(); cudaFree(d_offs); cudaFree(d_bytes);
+    cudaFree(d_offs);
     return rc;
 }
 
@@ -119,33 +140,24 @@ extern "C" int bpe_load_text_gpt4(bpe_handle *h, const uint8_t *bytes, uint64_t 
     if (rc) return rc;
     u64 chunks = 0;
     if (n) {
-        unsigned char *d_bytes = nullptr;
-        CU(cudaMalloc(&d_bytes, n));
-        cudaError_t e = cudaMemcpyAsync(d_bytes, bytes, n, cudaMemcpyHostToDevice, h->stream);
-        if (e != cudaSuccess) { cudaFree(d_bytes); return fail(h, BPE_ERR_CUDA, cudaGetErrorString(e)); }
-        h->tm.h2d_bytes = n;
         SplitWork W;
-        rc = split_flags(h, d_bytes, n, W);
-        if (!rc) {
-            k_widen_marked<<<h->sms * 8, 256, 0, h->stream>>>(d_bytes, W.flag, h->buf[0], n);
-            h->tm.kernel_launches += 1;
-            if (n_chunks) {   // only counted on request (one extra pass over the flags)
-                const u32 ntiles = (u32)((n + SP_TILE - 1) / SP_TILE);
-                u32 *part = nullptr; u64 *excl = nullptr, *d_total = nullptr;
-                if (cudaMalloc(&part, (size_t)ntiles * 4) == cudaSuccess && cudaMalloc(&excl, (size_t)ntiles * 8) == cudaSuccess &&
-                    cudaMalloc(&d_total, 8) == cudaSuccess) {
-                    k_flag_reduce<<<ntiles, SP_THREADS, 0, h->stream>>>(W.flag, n, part);
-                    k_flag_scan_parts<<<1, 1024, 0, h->stream>>>(part, excl, ntiles, d_total);
-                    cudaMemcpyAsync(&chunks, d_total, 8, cudaMemcpyDeviceToHost, h->stream);
-                }
-                cudaStreamSynchronize(h->stream);
-                cudaFree(part); cudaFree(excl); cudaFree(d_total);
-            }
-            e = cudaStreamSynchronize(h->stream);
-            if (e != cudaSuccess) rc = fail(h, BPE_ERR_CUDA, std::string("bpe_load_text_gpt4: ") + cudaGetErrorString(e));
-        }
-        W.release(); cudaFree(d_bytes);
+        rc = split_flags(h, bytes, n, W);
         if (rc) return rc;
+        k_widen_marked<<<h->sms * 8, 256, 0, h->stream>>>(W.bytes, W.flag, h->buf[0], n);
+        h->tm.kernel_launches += 1;
+        if (n_chunks) {   // only counted on request (one extra pass over the flags)
+            const u32 ntiles = (u32)((n + SP_TILE - 1) / SP_TILE);
+            u32 *part = nullptr; u64 *excl = nullptr, *d_total = nullptr;
+            if (cudaMalloc(&part, (size_t)ntiles * 4) == cudaSuccess && cudaMalloc(&excl, (size_t)ntiles * 8) == cudaSuccess &&
+                cudaMalloc(&d_total, 8) == cudaSuccess) {
+                k_flag_reduce<<<ntiles, SP_THREADS, 0, h->stream>>>(W.flag, n, part);
+                k_flag_scan_parts<<<1, 1024, 0, h->stream>>>(part, excl, ntiles, d_total);
+                cudaMemcpyAsync(&chunks, d_total, 8, cudaMemcpyDeviceToHost, h->stream);
+            }
+            cudaStreamSynchronize(h->stream);
+            cudaFree(part); cudaFree(excl); cudaFree(d_total);
+        }
+        CU(cudaGetLastError());
     }
     if (n_chunks) *n_chunks = chunks;
     if ((rc = reset_ctl_for_stream(h, n))) return rc;
