@@ -193,10 +193,16 @@ def bench_sharded(args, rank, world, local):
 
     # ---- device-resident: W warm-up merges, then exactly K timed ----
     eng.load_stream(raw, offs)
+    P = 8   # extra merges after the timed ones, with CUDA events between the phases of every step
     tr = ShardedTrainer(step, rank, world, poll_every=16)
-    tr.prepare(W + K)
+    tr.prepare(W + K + P)
     tr.run(W)
     sync_all()
+    sampler = None
+    if rank == 0:
+        from bench import ClockSampler
+        sampler = ClockSampler(local)
+        sampler.start()
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     ev0.record(step.stream)
     t0 = time.perf_counter()
@@ -204,11 +210,28 @@ def bench_sharded(args, rank, world, local):
     ev1.record(step.stream)
     sync_all()
     wall = time.perf_counter() - t0
+    clocks = sampler.stop() if sampler else None
+    # where a step's time goes: select | all-reduce MIN | merge pass | all-reduce SUM | apply (rank 0's view;
+    # a collective's share includes waiting for the slower rank)
+    marks = []
+    with tr._ctx():
+        for _ in range(P):
+            e = [torch.cuda.Event(enable_timing=True) for _ in range(6)]
+            e[0].record(); tr.eng.select(tr.cand, tr.rank)
+            e[1].record(); tr._allreduce(tr.cand[:1], dist.ReduceOp.MIN)
+            e[2].record(); tr.eng.merge(tr.cand, tr.delta)
+            e[3].record(); tr._allreduce(tr.delta, dist.ReduceOp.SUM)
+            e[4].record(); tr.eng.apply(tr.delta)
+            e[5].record(); marks.append(e)
+        tr.done, _ = tr.eng.poll()
+    sync_all()
+    names = ["select", "allreduce_min", "merge", "allreduce_sum", "apply"]
+    phases = {nm: float(np.mean([m[i].elapsed_time(m[i + 1]) for m in marks])) for i, nm in enumerate(names)}
     t_loop = torch.tensor([ev0.elapsed_time(ev1) / 1e3], device="cuda")   # kernels + collectives share torch's stream
     dist.all_reduce(t_loop, op=dist.ReduceOp.MAX)
     pairs, counts, n = tr.result()
     tm = eng.timing()
-    ok = (n == W + K) and np.array_equal(pairs, pairs_e2e)
+    ok = (n == W + K + P) and np.array_equal(pairs[: W + K], pairs_e2e)
     if rank == 0:
         from bench import measured_peak
         t = float(t_loop.item())
@@ -230,6 +253,7 @@ def bench_sharded(args, rank, world, local):
                        "timing": "CUDA events on the shared torch stream, max over ranks, barrier + synchronize on both sides"},
             "merges_per_s": K / t, "wall_ms_per_step": wall / K * 1e3,
             "gpu_launches": int(tm["kernel_launches"]),
+            "clocks": clocks, "phases_ms": phases,
             "roofline": {"bound": "hbm", "kernel": "k_merge_seg (rank 0; rate over the whole step incl. collectives)", "achieved": bytes_per_launch / (k_ms / 1e3) / 1e9,
                          "peak": peak, "unit": "GB/s", "frac": bytes_per_launch / (k_ms / 1e3) / 1e9 / peak, "traffic": None,
                          "peak_source": peak_src, "ms_per_launch": k_ms},
