@@ -76,29 +76,47 @@ class ClockSampler:
 
     def __init__(self, gpu=0):
         self.gpu, self.rows, self.proc = gpu, [], None
+        self.t_begin = self.t_end = None
 
     def start(self):
+        """Start sampling (nvidia-smi needs ~0.2 s to produce its first line: call this well before the timed region)."""
         try:
             self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
-                                          "-lms", "100", "-i", str(self.gpu)], stdout=subprocess.PIPE, text=True)
+                                          "-lms", "20", "-i", str(self.gpu)], stdout=subprocess.PIPE, text=True)
             self.t = threading.Thread(target=self._read, daemon=True)
             self.t.start()
         except Exception:  # noqa: BLE001
             self.proc = None
 
+    def begin(self):
+        self.t_begin = time.perf_counter()
+
+    def end(self):
+        self.t_end = time.perf_counter()
+
     def _read(self):
         for line in self.proc.stdout:
-            self.rows.append([x.strip() for x in line.split(",")])
+            self.rows.append([time.perf_counter()] + [x.strip() for x in line.split(",")])
 
     def stop(self):
         if not self.proc:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
-        time.sleep(0.15)
+        if self.t_end is None:
+            self.t_end = time.perf_counter()
+        time.sleep(0.1)
         self.proc.terminate()
         try:
             self.proc.wait(timeout=5)
         except Exception:  # noqa: BLE001
             self.proc.kill()
+        lo = self.t_begin if self.t_begin is not None else 0.0
+        rows = [r[1:] for r in self.rows if lo <= r[0] <= self.t_end + 0.03]
+        window = "timed region"
+        if not rows and self.rows:   # region shorter than the sampling period: the sample nearest to it
+            mid = 0.5 * (lo + self.t_end)
+            rows = [min(self.rows, key=lambda r: abs(r[0] - mid))[1:]]
+            window = "nearest sample to the timed region"
+        self.rows = rows
         sm = [float(r[1]) for r in self.rows if len(r) >= 9 and r[1].replace(".", "").isdigit()]
         mx = [float(r[2]) for r in self.rows if len(r) >= 9 and r[2].replace(".", "").isdigit()]
         reasons = set()
@@ -109,7 +127,7 @@ class ClockSampler:
                     if v.lower().startswith("active"):
                         reasons.add(nm)
         return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
-                "reasons": sorted(reasons), "samples": len(sm)}
+                "reasons": sorted(reasons), "samples": len(sm), "window": window}
 
 
 def make_corpus(size_bytes, seed):
@@ -236,6 +254,8 @@ def run_ours(args):
     if args.merge_impl is not None:
         eng.set_option(E.OPT_MERGE_IMPL, args.merge_impl)
 
+    sampler = ClockSampler(local)
+    sampler.start()   # sampling runs from here; only the rows inside the timed region are reported
     # ---- e2e: C-ABI calls from host buffers (upload + device split + W+K merges + merges back) ----
     pinned = pin_host(raw)
     # untimed warm-up of the same calls (class tables, first-touch of the big device allocations, clocks)
@@ -259,14 +279,14 @@ def run_ours(args):
 
     # ---- device-resident: W warm-up steps, then exactly K timed steps ----
     eng.load_stream(raw, offs)
-    sampler = ClockSampler(local)
     eng.train(W)
     torch.cuda.synchronize()
-    sampler.start()
+    sampler.begin()
     t0 = time.perf_counter()
     pairs, counts, done = eng.train(K, first_idx=256 + W)
     torch.cuda.synchronize()
     wall = time.perf_counter() - t0
+    sampler.end()
     clocks = sampler.stop()
     tm = eng.timing()
     assert done == K

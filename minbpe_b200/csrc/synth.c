@@ -143,16 +143,16 @@ static void gen_block(const lexicon *L, uint64_t seed, uint64_t k, uint8_t *out)
     memset(out + n, ' ', BLOCK - n);
 }
 
-typedef struct { const lexicon *L; uint64_t seed, k0, k1; uint8_t *out; uint64_t nbytes; } job;
+typedef struct { const lexicon *L; uint64_t seed, k0, k1, kbase; uint8_t *out; uint64_t nbytes; } job;
 
 static void *worker(void *arg) {
     job *j = (job *)arg;
     uint8_t *buf = (uint8_t *)malloc(BLOCK);
     for (uint64_t k = j->k0; k < j->k1; ++k) {
         uint64_t off = k * (uint64_t)BLOCK;
-        if (off + BLOCK <= j->nbytes) gen_block(j->L, j->seed, k, j->out + off);
+        if (off + BLOCK <= j->nbytes) gen_block(j->L, j->seed, j->kbase + k, j->out + off);
         else { /* final partial block: generate whole, copy a prefix cut at a char boundary */
-            gen_block(j->L, j->seed, k, buf);
+            gen_block(j->L, j->seed, j->kbase + k, buf);
             uint64_t m = j->nbytes - off;
             uint64_t cut = m;
             while (cut > 0 && (buf[cut] & 0xC0) == 0x80) --cut; /* buf[cut] would start mid-char */
@@ -164,8 +164,10 @@ static void *worker(void *arg) {
     return NULL;
 }
 
-/* Fill out[0..nbytes) with the corpus for `seed`.  Returns 0 on success. */
-int bpe_synth_generate(uint64_t seed, uint8_t *out, uint64_t nbytes, int n_threads) {
+/* Fill out[0..nbytes) with the 1 MiB blocks first_block, first_block+1, ... of the corpus for `seed`
+ * (a contiguous shard of that corpus: same lexicon, same text as a full generation would put there).
+ * Returns 0 on success. */
+int bpe_synth_generate_at(uint64_t seed, uint64_t first_block, uint8_t *out, uint64_t nbytes, int n_threads) {
     lexicon *L = (lexicon *)malloc(sizeof(lexicon));
     if (!L) return -1;
     build_lexicon(L, seed);
@@ -175,10 +177,15 @@ int bpe_synth_generate(uint64_t seed, uint8_t *out, uint64_t nbytes, int n_threa
     pthread_t *th = (pthread_t *)malloc(sizeof(pthread_t) * n_threads);
     job *jobs = (job *)malloc(sizeof(job) * n_threads);
     for (int t = 0; t < n_threads; ++t) {
-        jobs[t] = (job){L, seed, nblocks * t / n_threads, nblocks * (t + 1) / n_threads, out, nbytes};
+        jobs[t] = (job){L, seed, nblocks * t / n_threads, nblocks * (t + 1) / n_threads, first_block, out, nbytes};
         pthread_create(&th[t], NULL, worker, &jobs[t]);
     }
     for (int t = 0; t < n_threads; ++t) pthread_join(th[t], NULL);
     free(th); free(jobs); free(L);
     return 0;
+}
+
+/* Fill out[0..nbytes) with the corpus for `seed` from its beginning. */
+int bpe_synth_generate(uint64_t seed, uint8_t *out, uint64_t nbytes, int n_threads) {
+    return bpe_synth_generate_at(seed, 0, out, nbytes, n_threads);
 }

@@ -158,7 +158,8 @@ def bench_sharded(args, rank, world, local):
     size = args.size_mib << 20
     K, W = args.steps, args.warmup
     t0 = time.time()
-    raw = generate(args.seed + rank, size, threads=max(1, (os.cpu_count() or 8) // world))
+    # rank r holds MiB [r*size_mib, (r+1)*size_mib) of ONE corpus (one lexicon); rank 0's shard is the N=1 workload
+    raw = generate(args.seed, size, threads=max(1, (os.cpu_count() or 8) // world), first_block=rank * args.size_mib)
     offs = chunk_offsets(GPT4_SPLIT_PATTERN, raw, workers=max(1, min(64, (os.cpu_count() or 8) // world)))
     prep_s = time.time() - t0
 
@@ -167,6 +168,11 @@ def bench_sharded(args, rank, world, local):
     eng = E.Engine(local)
     eng.set_option(E.OPT_KERNEL_TIMING, 1)
     step = GpuStepEngine(eng, local)
+    sampler = None
+    if rank == 0:
+        from bench import ClockSampler
+        sampler = ClockSampler(local)
+        sampler.start()   # sampling runs from here; only the rows inside the timed region are reported
 
     def sync_all():
         torch.cuda.synchronize()
@@ -198,11 +204,8 @@ def bench_sharded(args, rank, world, local):
     tr.prepare(W + K + P)
     tr.run(W)
     sync_all()
-    sampler = None
-    if rank == 0:
-        from bench import ClockSampler
-        sampler = ClockSampler(local)
-        sampler.start()
+    if sampler:
+        sampler.begin()
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     ev0.record(step.stream)
     t0 = time.perf_counter()
@@ -210,6 +213,8 @@ def bench_sharded(args, rank, world, local):
     ev1.record(step.stream)
     sync_all()
     wall = time.perf_counter() - t0
+    if sampler:
+        sampler.end()
     clocks = sampler.stop() if sampler else None
     # where a step's time goes: select | all-reduce MIN | merge pass | all-reduce SUM | apply (rank 0's view;
     # a collective's share includes waiting for the slower rank)
@@ -227,6 +232,8 @@ def bench_sharded(args, rank, world, local):
     sync_all()
     names = ["select", "allreduce_min", "merge", "allreduce_sum", "apply"]
     phases = {nm: float(np.mean([m[i].elapsed_time(m[i + 1]) for m in marks])) for i, nm in enumerate(names)}
+    all_phases = [None] * world
+    dist.all_gather_object(all_phases, phases)
     t_loop = torch.tensor([ev0.elapsed_time(ev1) / 1e3], device="cuda")   # kernels + collectives share torch's stream
     dist.all_reduce(t_loop, op=dist.ReduceOp.MAX)
     pairs, counts, n = tr.result()
@@ -246,14 +253,14 @@ def bench_sharded(args, rank, world, local):
             "steps": K, "warmup": W, "ms_per_step": t / K * 1e3, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "int32", "data": "synthetic",
             "config": {"workload": f"RegexTokenizer.train merge loop (GPT-4 split), {args.size_mib} MiB synthetic UTF-8 per GPU "
-                                   f"(seed {args.seed}+rank), contiguous shards of one {args.size_mib * world} MiB corpus, "
+                                   f"(seed {args.seed}), contiguous shards of one {args.size_mib * world} MiB corpus, "
                                    f"merge steps {W}..{W + K - 1}; per merge: NCCL all-reduce MIN (8 B) + SUM (delta vector)",
                        "parallelism": f"shard{world}", "prep_s": round(prep_s, 1), "consistent": bool(ok),
                        "l2": "per-GPU stream >> 126 MB L2, re-read from HBM every step",
                        "timing": "CUDA events on the shared torch stream, max over ranks, barrier + synchronize on both sides"},
             "merges_per_s": K / t, "wall_ms_per_step": wall / K * 1e3,
             "gpu_launches": int(tm["kernel_launches"]),
-            "clocks": clocks, "phases_ms": phases,
+            "clocks": clocks, "phases_ms": {f"rank{r}": ph for r, ph in enumerate(all_phases)},
             "roofline": {"bound": "hbm", "kernel": "k_merge_seg (rank 0; rate over the whole step incl. collectives)", "achieved": bytes_per_launch / (k_ms / 1e3) / 1e9,
                          "peak": peak, "unit": "GB/s", "frac": bytes_per_launch / (k_ms / 1e3) / 1e9 / peak, "traffic": None,
                          "peak_source": peak_src, "ms_per_launch": k_ms},
