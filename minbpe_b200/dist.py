@@ -218,6 +218,7 @@ def bench_sharded(args, rank, world, local):
     clocks = sampler.stop() if sampler else None
     # where a step's time goes: select | all-reduce MIN | merge pass | all-reduce SUM | apply (rank 0's view;
     # a collective's share includes waiting for the slower rank)
+    sync_all()   # rank 0 has just spent 0.1 s stopping its clock sampler: do not bill that to rank 1's first collective
     marks = []
     with tr._ctx():
         for _ in range(P):
@@ -231,7 +232,7 @@ def bench_sharded(args, rank, world, local):
         tr.done, _ = tr.eng.poll()
     sync_all()
     names = ["select", "allreduce_min", "merge", "allreduce_sum", "apply"]
-    phases = {nm: float(np.mean([m[i].elapsed_time(m[i + 1]) for m in marks])) for i, nm in enumerate(names)}
+    phases = {nm: float(np.mean([m[i].elapsed_time(m[i + 1]) for m in marks[1:]])) for i, nm in enumerate(names)}
     all_phases = [None] * world
     dist.all_gather_object(all_phases, phases)
     t_loop = torch.tensor([ev0.elapsed_time(ev1) / 1e3], device="cuda")   # kernels + collectives share torch's stream

@@ -1,6 +1,6 @@
 #!/bin/bash
 # development helper: validation of the final tree on one GPU
-cd "$(dirname "$0")"
+cd "$(dirname "$0")/.."
 O=gpurun_out
 timeout 600 python -m pytest tests -x -q -m gpu 2>&1 | tail -3
 timeout 600 python bench.py > $O/bench_a.json 2> $O/bench_a.err; tail -c 700 $O/bench_a.json; tail -3 $O/bench_a.err

@@ -1,9 +1,9 @@
 #!/bin/bash
 # development helper (round-end validation on the GPU box): pick the fastest launch configuration of the merge
 # kernel among the prebuilt variants, then run the whole validation + measurement set with it.
-cd "$(dirname "$0")"
+cd "$(dirname "$0")/.."
 O=gpurun_out
-bash gpurun_variants.sh > $O/variants4.txt 2>&1
+bash tools/bench_variants.sh > $O/variants4.txt 2>&1
 cat $O/variants4.txt
 python - <<'PY' > $O/chosen.txt
 import re
