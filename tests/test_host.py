@@ -134,3 +134,15 @@ def test_split_text_matches_findall(taylorswift, pattern):
         assert bytes(data) == b"".join(chunks)
         got = [bytes(data)[int(a):int(b)] for a, b in zip(offs, list(offs[1:]) + [len(data)])] if len(offs) else []
         assert got == chunks
+
+
+def test_synthetic_shards_are_ranges_of_one_corpus():
+    """bench.py --gpus N gives rank r the r-th contiguous range of ONE corpus (minbpe_b200/synth.py first_block):
+    the shards concatenate to the text a single generation produces, and each is valid UTF-8 on its own."""
+    from minbpe_b200.synth import generate
+    full = generate(1337, 6 << 20, threads=3)
+    parts = [generate(1337, 2 << 20, threads=2, first_block=2 * r) for r in range(3)]
+    assert np.array_equal(np.concatenate(parts), full)
+    for p in parts:
+        p.tobytes().decode("utf-8")
+    assert not np.array_equal(parts[0], parts[1])
