@@ -251,8 +251,6 @@ def run_ours(args):
     torch.cuda.set_device(local)
     eng = E.Engine(local)
     eng.set_option(E.OPT_KERNEL_TIMING, 1)
-    if args.merge_impl is not None:
-        eng.set_option(E.OPT_MERGE_IMPL, args.merge_impl)
 
     sampler = ClockSampler(local)
     sampler.start()   # sampling runs from here; only the rows inside the timed region are reported
@@ -398,7 +396,6 @@ def main():
     ap.add_argument("--size-mib", type=int, default=1024, help="corpus bytes per GPU (MiB)")
     ap.add_argument("--seed", type=int, default=1337)
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--merge-impl", type=int, default=None, help="development switch (BPE_OPT_MERGE_IMPL)")
     ap.add_argument("--extras", action="store_true", help="side measurements (cfg2 wall time, encode throughput)")
     args = ap.parse_args()
     if args.warmup < 3 and args.impl == "ours":

@@ -185,8 +185,6 @@ int bpe_get_timing(bpe_handle *h, bpe_timing *out);
                                    instead of maintaining it incrementally (verification) */
 #define BPE_OPT_BATCH 3         /* max merge iterations enqueued per host synchronisation */
 #define BPE_OPT_TABLE_LOG2 4    /* log2 of the pair-count table capacity (0 = automatic) */
-#define BPE_OPT_MERGE_IMPL 5    /* development switch: 1 = warp-specialised TMA merge kernel
-                                   (default), 0 = the plain-load kernel it replaced */
 int bpe_set_option(bpe_handle *h, int opt, int64_t value);
 
 /* Test hook: live entries (count > 0) of the incrementally maintained pair-count table, in no

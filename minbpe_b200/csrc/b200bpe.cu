@@ -53,7 +53,7 @@ struct bpe_handle {
 
     // options
     int step_poll_every = 16;
-    int opt_kernel_timing = 0, opt_rescan = 0, opt_batch = 256, opt_table_log2 = 0, opt_merge_impl = 1;
+    int opt_kernel_timing = 0, opt_rescan = 0, opt_batch = 256, opt_table_log2 = 0;
 
     bpe_timing tm = {};
     std::vector<cudaEvent_t> ev_pool;  // per-launch timing of the fused merge kernel (BPE_OPT_KERNEL_TIMING)
@@ -200,7 +200,6 @@ extern "C" int bpe_set_option(bpe_handle *h, int opt, int64_t value) {
         case BPE_OPT_TABLE_LOG2:
             if (value != 0 && (value < 10 || value > 30)) return fail(h, BPE_ERR_ARG, "table log2 must be 0 or in [10,30]");
             h->opt_table_log2 = (int)value; break;
-        case BPE_OPT_MERGE_IMPL: h->opt_merge_impl = (int)value; break;  /* kept for ABI compatibility; unused */
         default: return fail(h, BPE_ERR_ARG, "unknown option");
     }
     return BPE_OK;

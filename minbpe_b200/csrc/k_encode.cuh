@@ -8,7 +8,7 @@
 //                    merge ranks from an open-addressing table that lives in L2/L1
 //   k_encode_long    one CTA per long chunk (<= ENC_LONG_MAX tokens), tokens in shared memory
 // Ids are written at the chunk's own byte offset in a buffer of n words, unused tail slots get
-// ENC_HOLE; k_compact_holes then squeezes every 4096-word segment in place and leaves segment
+// ENC_HOLE; k_compact_holes then squeezes every 512-word segment in place and leaves segment
 // counts in the edge records, so the ordinary pack (k_scan_counts + k_gather) produces the
 // contiguous id list.
 #pragma once
