@@ -48,3 +48,29 @@ def test_random_adversarial():
     for _ in range(2000):
         n = rnd.randint(0, 30)
         check("".join(chr(rnd.choice(rnd.choice(pools))) for _ in range(n)))
+
+
+def test_local_formulation():
+    """oracle/split_rules_local.py: the same rules from six segmented scans + neighbours at distance <= 2
+    (the form the next device splitter evaluates tile by tile) against `regex`."""
+    from oracle.split_rules_local import split as split_local
+
+    def check_local(text):
+        assert split_local(text) == GPT4.findall(text), text
+
+    for t in CASES:
+        check_local(t)
+    rnd = random.Random(777)
+    alphabet = list("ab'sSdDmMtTlLvVeErR 12\t\n\r!.,' 　é日ſ½") + ["  ", "\n\n", "'ll", "'ve", " '"]
+    for _ in range(4000):
+        check_local("".join(rnd.choice(alphabet) for _ in range(rnd.randint(0, 24))))
+    pools = [range(0x20, 0x7f), range(0xa0, 0x250), range(0x2000, 0x2070), range(0x3000, 0x3100),
+             [0x9, 0xa, 0xd, 0x20, 0x85, 0x1680, 0x2028, 0x2029, 0x202f, 0x205f]]
+    for _ in range(1000):
+        check_local("".join(chr(rnd.choice(rnd.choice(pools))) for _ in range(rnd.randint(0, 30))))
+
+
+def test_local_formulation_corpus(taylorswift):
+    from oracle.split_rules_local import split as split_local
+    text = taylorswift[:60000]
+    assert split_local(text) == GPT4.findall(text)
