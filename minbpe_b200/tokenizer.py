@@ -7,10 +7,13 @@ so callers and the reference's own tests work unchanged; the loops underneath ar
     train()            -> Engine.load_stream + Engine.train   (bpe_load_stream, bpe_train)
     encode*()          -> Engine.encode                        (bpe_encode)
     get_stats / merge  -> Engine.get_stats / Engine.merge      (bpe_get_stats, bpe_merge)
+    GPT-4 pre-split    -> Engine.load_text_gpt4 / split_gpt4   (bpe_load_text_gpt4, bpe_split_gpt4) for texts
+                          of at least 64 KiB; same chunks as regex.findall (tests/test_gpu_split.py)
 
-What stays on the host, as in the reference: the regex pre-split (third-party ``regex``
-module, regex.py:41,114), special-token splitting (regex.py:123-164), vocab construction and
-the save/load file format (base.py:88-165), decode (basic.py:51-55, regex.py:78-90).
+What stays on the host, as in the reference: the regex pre-split for any other pattern and for
+short texts (third-party ``regex`` module, regex.py:41,114), special-token splitting
+(regex.py:123-164), vocab construction and the save/load file format (base.py:88-165), decode
+(basic.py:51-55, regex.py:78-90).
 
 There is no CPU fallback: without libb200bpe.so and a B200 the device-backed calls raise.
 """
