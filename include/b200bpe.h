@@ -160,6 +160,16 @@ int bpe_step_poll(bpe_handle *h, int32_t *iters_done, int32_t *exhausted);
 /* Pairs and (global) counts of the merges performed so far. */
 int bpe_step_result(bpe_handle *h, int32_t *out_pairs, int64_t *out_counts, int32_t cap, int32_t *n_done);
 
+/* decode (basic.py:51-55, regex.py:78-90): out = vocab[ids[0]] + vocab[ids[1]] + ...  The vocabulary is
+ * passed flat: vocab_bytes (all token bytes back to back), vocab_start[V] and vocab_len[V] per id;
+ * vocab_len[id] = 0xffffffff marks an id that is not in the vocabulary.  *out_n = number of bytes (also
+ * set when BPE_ERR_CAPACITY is returned, so the caller can size the buffer and call again).  An id that
+ * is negative, >= V or marked absent ends the call with BPE_ERR_ARG and *bad_index = its position (the
+ * reference raises ValueError in RegexTokenizer.decode, KeyError in BasicTokenizer.decode). */
+int bpe_decode(bpe_handle *h, const int32_t *ids, uint64_t n_ids, const uint8_t *vocab_bytes, uint64_t vocab_nbytes,
+               const uint64_t *vocab_start, const uint32_t *vocab_len, int32_t V, uint8_t *out, uint64_t cap,
+               uint64_t *out_n, int64_t *bad_index);
+
 /* ---- measurement --------------------------------------------------------------------------- */
 
 typedef struct {

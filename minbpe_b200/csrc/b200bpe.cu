@@ -19,6 +19,7 @@
 #include "k_stats.cuh"
 #include "k_encode.cuh"
 #include "k_split.cuh"
+#include "k_decode.cuh"
 
 #define BPE_ABI_VERSION 1
 
@@ -742,3 +743,4 @@ extern "C" int bpe_debug_table(bpe_handle *h, int32_t *pairs, int64_t *counts, u
 #include "encode_host.inl"
 #include "step_host.inl"
 #include "split_host.inl"
+#include "decode_host.inl"

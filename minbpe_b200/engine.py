@@ -61,6 +61,7 @@ def load_library():
         "bpe_debug_table": ([vp, vp, vp, u64, P(u64)], ci),
         "bpe_gpt4_tables": ([vp, vp, vp], ci),
         "bpe_split_gpt4": ([vp, vp, u64, vp, u64, P(u64)], ci),
+        "bpe_decode": ([vp, vp, u64, vp, u64, vp, vp, ctypes.c_int32, vp, u64, P(u64), P(ctypes.c_int64)], ci),
         "bpe_load_text_gpt4": ([vp, vp, u64, P(u64)], ci),
         "bpe_set_stream": ([vp, vp], ci),
         "bpe_step_begin": ([vp, vp], ci),
@@ -181,6 +182,29 @@ class Engine:
                                          _ptr(m) if m.size else None, m.shape[0], _ptr(perm), _ptr(out), out.size,
                                          ctypes.byref(n)), "bpe_encode")
         return out[: n.value]
+
+    def decode(self, ids, vocab_bytes, vocab_start, vocab_len):
+        """-> (bytes, -1), or (None, i) when ids[i] is not in the vocabulary.  vocab_*: the flat vocabulary of
+        bpe_decode (include/b200bpe.h)."""
+        a = np.ascontiguousarray(ids, dtype=np.int32)
+        vb = np.ascontiguousarray(vocab_bytes, dtype=np.uint8)
+        vs = np.ascontiguousarray(vocab_start, dtype=np.uint64)
+        vl = np.ascontiguousarray(vocab_len, dtype=np.uint32)
+        n, bad = ctypes.c_uint64(), ctypes.c_int64(-1)
+        cap = int(a.size) * 4 + 64
+        for _ in range(2):
+            out = np.empty(cap, dtype=np.uint8)
+            rc = self._lib.bpe_decode(self._h, _ptr(a) if a.size else None, a.size, _ptr(vb) if vb.size else None, vb.size,
+                                      _ptr(vs) if vs.size else None, _ptr(vl) if vl.size else None, int(vl.size), _ptr(out), cap,
+                                      ctypes.byref(n), ctypes.byref(bad))
+            if rc == -2 and bad.value >= 0:      # BPE_ERR_ARG with a position: an id outside the vocabulary
+                return None, int(bad.value)
+            if rc == -4 and n.value > cap:       # BPE_ERR_CAPACITY: the exact size is known now
+                cap = int(n.value)
+                continue
+            self._check(rc, "bpe_decode")
+            return out[: n.value].tobytes(), -1
+        raise EngineError("bpe_decode: capacity retry failed")
 
     # ---- measurement / options ----
     def timing(self):

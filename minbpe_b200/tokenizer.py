@@ -159,6 +159,30 @@ class Tokenizer:
     def _build_vocab(self):
         return _vocab_from_merges(self.merges, self.special_tokens)
 
+    # id lists at least this long are decoded on the GPU (bpe_decode) when this process already holds an engine
+    # (decode is a host function in the reference and must keep working on a machine without a GPU, e.g. for a
+    # model that was only loaded); same bytes as the joins below
+    DEVICE_DECODE_MIN_IDS = 1 << 16
+
+    def _decode_on_device(self, n_ids):
+        return n_ids >= self.DEVICE_DECODE_MIN_IDS and (self._engine is not None or _shared_engine is not None)
+
+    def _device_decode(self, ids, table):
+        """table: {id: bytes}.  Returns (bytes, -1) or (None, position of the first id that is not in the table)."""
+        top = max(table) + 1 if table else 0
+        lens = np.full(top, 0xFFFFFFFF, dtype=np.uint32)
+        starts = np.zeros(top, dtype=np.uint64)
+        blob, pos = [], 0
+        for idx, bts in table.items():
+            if 0 <= idx < top:
+                starts[idx], lens[idx] = pos, len(bts)
+                blob.append(bts)
+                pos += len(bts)
+        arr = np.asarray(ids)
+        if arr.dtype.kind not in "iu" or (arr.size and (arr.min() < -(2 ** 31) or arr.max() >= 2 ** 31)):
+            return None, next(i for i, x in enumerate(ids) if not (isinstance(x, (int, np.integer)) and -(2 ** 31) <= x < 2 ** 31))
+        return self.engine.decode(arr.astype(np.int32), np.frombuffer(b"".join(blob), dtype=np.uint8), starts, lens)
+
     def save(self, file_prefix):
         """base.py:97-138.  ``<prefix>.model`` (version, pattern, specials, one merge per line)
         and ``<prefix>.vocab`` (human readable, lossy)."""
@@ -206,6 +230,11 @@ class BasicTokenizer(Tokenizer):
         self._run_training(text.encode("utf-8"), None, vocab_size, verbose)
 
     def decode(self, ids):
+        if self._decode_on_device(len(ids)):
+            data, bad = self._device_decode(ids, self.vocab)
+            if data is None:
+                raise KeyError(ids[bad])          # what self.vocab[idx] raises (basic.py:53)
+            return data.decode("utf-8", errors="replace")
         return b"".join(self.vocab[idx] for idx in ids).decode("utf-8", errors="replace")
 
     def encode(self, text):
@@ -273,6 +302,13 @@ class RegexTokenizer(Tokenizer):
         self.inverse_special_tokens = {idx: text for text, idx in special_tokens.items()}
 
     def decode(self, ids):
+        if self._decode_on_device(len(ids)):
+            table = {idx: text.encode("utf-8") for idx, text in self.inverse_special_tokens.items()}
+            table.update(self.vocab)              # regex.py:81-86: the vocabulary first, then the special tokens
+            data, bad = self._device_decode(ids, table)
+            if data is None:
+                raise ValueError(f"invalid token id: {ids[bad]}")
+            return data.decode("utf-8", errors="replace")
         parts = []
         for idx in ids:
             if idx in self.vocab:
