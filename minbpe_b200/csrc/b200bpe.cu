@@ -49,6 +49,7 @@ struct bpe_handle {
     int *log_pairs = nullptr; long long *log_counts = nullptr; int log_cap = 0;
     Best *partials = nullptr;
     unsigned char *d_cls = nullptr, *d_contr = nullptr;   // code-point class / contraction tables of the GPT-4 splitter
+    u32 *d_present = nullptr;   // sharded loop: bitmap of pair hashes that have occurred in this shard (k_stats.cuh)
     unsigned char *split_slab = nullptr; u64 split_cap = 0;   // working set of the splitter, kept between calls (split_host.inl)
     int argmax_grid = 0, merge_grid = 0, merge_grid_same = 0, merge_grid_seg = 0, ff_grid = 0;
 
@@ -184,6 +185,7 @@ extern "C" int bpe_destroy(bpe_handle *h) {
     if (h->partials) cudaFree(h->partials);
     if (h->d_cls) cudaFree(h->d_cls);
     if (h->d_contr) cudaFree(h->d_contr);
+    if (h->d_present) cudaFree(h->d_present);
     if (h->split_slab) cudaFree(h->split_slab);
     if (h->ctl) cudaFree(h->ctl);
     if (h->h_ctl) cudaFreeHost(h->h_ctl);

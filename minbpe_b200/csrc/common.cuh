@@ -92,7 +92,7 @@ struct Ctl {
     u32 contig;       // 1: the current buffer is a contiguous stream whose edge records are stale
     u64 table_limit;  // k_apply_delta stops inserting at this many occupied slots ...
     u32 overflow;     // ... and raises this; the host grows the table and re-runs the apply
-    u32 pad1;
+    u32 tie_local;    // sharded loop: 1 = some pair tied at the max may occur in this rank's shard (k_tie_present)
 };
 
 // ---- segmented stream ------------------------------------------------------------------------

@@ -242,6 +242,7 @@ __global__ void __launch_bounds__(256) k_argmax(Table t, Ctl *ctl, Best *partial
         ctl->argmax_exit = 0;
         ctl->best_count = r.count; ctl->best_slot = r.slot; ctl->n_tied = r.tied;
         ctl->found_pos = POS_NONE;
+        ctl->tie_local = 0;
         if (r.count == 0) ctl->done = 1;                    // max({}) -> ValueError in the reference
         else if (r.tied == 1) {
             const u64 key = t.keys[r.slot];
@@ -264,7 +265,8 @@ __global__ void __launch_bounds__(256) k_find_first(const u32 *__restrict__ buf0
     if (ctl->done || ctl->overflow || ctl->iter >= ctl->max_iter || ctl->n_tied <= 1) return;
     const u32 *w = ctl->cur ? buf1 : buf0;
     const Edge *e = edges_cur(ctl, e0, e1);
-    const u32 nseg = ctl->nseg;
+    // sharded loop: none of the tied pairs has ever occurred in this shard -> nothing to scan, answer "not here"
+    const u32 nseg = (sharded && !ctl->tie_local) ? 0u : ctl->nseg;
     const u64 best = ctl->best_count;
     __shared__ bool last;
     __shared__ u64 s_found;
@@ -304,6 +306,46 @@ __global__ void __launch_bounds__(256) k_find_first(const u32 *__restrict__ buf0
             const u32 right = (i + 1 < e[sg].count) ? w[p + 1] : seg_next_first(e, sg, nseg);
             record_selection(ctl, (int)(w[p] & TOK_MASK), (int)right, best, log_pairs, log_counts);
         }
+    }
+}
+
+// =============================================================================================
+// Sharded loop: "may this pair occur in MY shard?"  A rank keeps a bitmap over pair hashes with a bit
+// for every pair that has ever existed in its shard (the byte pairs of iteration 0, then the pairs
+// each local merge creates: (x,z) for L[x] > 0, (z,y) for R[y] > 0, (z,z) for ZZ > 0 — the only
+// ways a pair can appear).  Bits are never cleared, so the answer is conservative: a set bit costs
+// at most the scan that was done unconditionally before; a clear bit proves absence.  On a tie whose
+// pairs live only in other ranks' shards, this rank skips the scan of its whole shard.
+// =============================================================================================
+#define PRESENT_LOG2 24
+__device__ __forceinline__ u32 present_hash(u64 key) { return (u32)(hash64(key) >> 24) & ((1u << PRESENT_LOG2) - 1u); }
+__device__ __forceinline__ void present_set(u32 *bm, u64 key) { const u32 x = present_hash(key); atomicOr(&bm[x >> 5], 1u << (x & 31u)); }
+__device__ __forceinline__ bool present_get(const u32 *bm, u64 key) { const u32 x = present_hash(key); return (bm[x >> 5] >> (x & 31u)) & 1u; }
+
+__global__ void k_present_init(const ull *__restrict__ dense, u32 *__restrict__ bm) {
+    const u32 i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < 65536u && dense[i]) present_set(bm, pack_pair(i >> 8, i & 255u));
+}
+
+// after a merge, from the LOCAL delta vector (before it is summed across ranks)
+__global__ void k_present_update(const ull *__restrict__ delta, u32 V, const Ctl *__restrict__ ctl, u32 *__restrict__ bm) {
+    if (ctl->done || ctl->overflow || ctl->a < 0) return;
+    const u32 z = (u32)ctl->z;
+    const u32 x = blockIdx.x * blockDim.x + threadIdx.x;
+    if (x < V) {
+        if (delta[x]) present_set(bm, pack_pair(x, z));
+        if (delta[V + x]) present_set(bm, pack_pair(z, x));
+    }
+    if (x == 0 && delta[2ull * V]) present_set(bm, pack_pair(z, z));
+}
+
+// on a tie: does any pair at the max count possibly occur in this shard?
+__global__ void __launch_bounds__(256) k_tie_present(Table t, Ctl *ctl, const u32 *__restrict__ bm) {
+    if (ctl->done || ctl->overflow || ctl->iter >= ctl->max_iter || ctl->n_tied <= 1) return;
+    const u64 best = ctl->best_count;
+    for (u64 s = (u64)blockIdx.x * blockDim.x + threadIdx.x; s <= t.mask; s += (u64)gridDim.x * blockDim.x) {
+        const u64 key = t.keys[s];
+        if (key != KEY_EMPTY && t.counts[s] == best && present_get(bm, key)) ctl->tie_local = 1;
     }
 }
 

@@ -28,8 +28,12 @@ extern "C" int bpe_step_begin(bpe_handle *h, uint64_t *dense_dev) {
     CU(cudaMemsetAsync(dense_dev, 0, 65536 * 8, h->stream));
     CU(cudaMemsetAsync(h->d_err, 0, 4, h->stream));
     k_hist_dense<<<h->sms * 3, 256, 0, h->stream>>>(h->buf[0], h->buf[1], h->ctl, h->edge[0], h->edge[1], (ull *)dense_dev, h->d_err);
+    // which pairs occur in THIS shard (before the caller sums the histogram across ranks)
+    if (!h->d_present) CU(cudaMalloc(&h->d_present, (1u << PRESENT_LOG2) / 8));
+    CU(cudaMemsetAsync(h->d_present, 0, (1u << PRESENT_LOG2) / 8, h->stream));
+    k_present_init<<<65536 / 256, 256, 0, h->stream>>>((const ull *)dense_dev, h->d_present);
     CU(cudaGetLastError());
-    h->tm.kernel_launches = 1;
+    h->tm.kernel_launches = 2;
     return BPE_OK;
 }
 
@@ -91,10 +95,11 @@ extern "C" int bpe_step_table(bpe_handle *h, const uint64_t *dense_dev, int32_t 
 extern "C" int bpe_step_select(bpe_handle *h, int64_t *cand_dev, int32_t rank) {
     if (!h || !cand_dev || rank < 0 || rank >= 32) return BPE_ERR_ARG;
     k_argmax<<<h->argmax_grid, 256, 0, h->stream>>>(h->table, h->ctl, h->partials, h->log_pairs, h->log_counts);
+    k_tie_present<<<h->argmax_grid, 256, 0, h->stream>>>(h->table, h->ctl, h->d_present);
     k_find_first<<<h->ff_grid, 256, 0, h->stream>>>(h->buf[0], h->buf[1], h->edge[0], h->edge[1], h->table, h->ctl,
                                                     h->log_pairs, h->log_counts, 1);
     k_pack_candidate<<<1, 1, 0, h->stream>>>(h->ctl, (long long *)cand_dev, rank);
-    h->tm.kernel_launches += 3;
+    h->tm.kernel_launches += 4;
     CU(cudaGetLastError());
     return BPE_OK;
 }
@@ -104,6 +109,9 @@ extern "C" int bpe_step_merge(bpe_handle *h, const int64_t *cand_dev, uint64_t *
     k_commit_candidate<<<1, 1, 0, h->stream>>>(h->ctl, (const long long *)cand_dev, h->log_pairs, h->log_counts);
     h->tm.kernel_launches += 1;
     timed_merge(h, (ull *)delta_dev);
+    // pairs this merge created in THIS shard (the delta is still local here; the caller sums it next)
+    k_present_update<<<(h->V + 255) / 256, 256, 0, h->stream>>>((const ull *)delta_dev, h->V, h->ctl, h->d_present);
+    h->tm.kernel_launches += 1;
     CU(cudaGetLastError());
     return BPE_OK;
 }
