@@ -14,12 +14,11 @@ extern "C" int bpe_gpt4_tables(bpe_handle *h, const uint8_t *cls_table, const ui
 }
 
 // Working set of one split call, carved out of a slab that stays with the handle (grow-only; given
-// back when the stream buffers have to grow, and in bpe_destroy): 23 bytes per text byte, so
-// allocating and freeing it on every call costs more than the kernels.
+// back when the stream buffers have to grow, and in bpe_destroy): the text, its 1-byte class array,
+// the flag bytes (offsets path only) and the tile aggregates — 3 bytes per text byte.
 struct SplitWork {
     unsigned char *bytes = nullptr, *meta = nullptr, *flag = nullptr;
-    u32 *rs = nullptr, *nl = nullptr, *cnt = nullptr, *re = nullptr, *nnl = nullptr;
-    Fwd *fpart = nullptr; Bwd *bpart = nullptr;
+    SplFwd *fpart = nullptr; SplBwd *bpart = nullptr;
 };
 
 static void split_slab_release(bpe_handle *h) {
@@ -30,8 +29,8 @@ static void split_slab_release(bpe_handle *h) {
 static int split_carve(bpe_handle *h, u64 n, SplitWork &W) {
     const u64 a = (n + 255) & ~255ull;
     const u64 ntiles = (n + SP_TILE - 1) / SP_TILE;
-    const u64 parts = ((ntiles * sizeof(Fwd) + 255) & ~255ull) + ((ntiles * sizeof(Bwd) + 255) & ~255ull);
-    const u64 need = 3 * a + 5 * 4 * a + parts + 256;
+    const u64 fbytes = (ntiles * sizeof(SplFwd) + 255) & ~255ull, bbytes = (ntiles * sizeof(SplBwd) + 255) & ~255ull;
+    const u64 need = 3 * a + fbytes + bbytes + 256;
     if (need > h->split_cap) {
         split_slab_release(h);
         cudaError_t e = cudaMalloc(&h->split_slab, need);
@@ -42,18 +41,14 @@ static int split_carve(bpe_handle *h, u64 n, SplitWork &W) {
     W.bytes = p; p += a;
     W.meta = p; p += a;
     W.flag = p; p += a;
-    W.rs = (u32 *)p; p += 4 * a;
-    W.nl = (u32 *)p; p += 4 * a;
-    W.cnt = (u32 *)p; p += 4 * a;
-    W.re = (u32 *)p; p += 4 * a;
-    W.nnl = (u32 *)p; p += 4 * a;
-    W.fpart = (Fwd *)p; p += (ntiles * sizeof(Fwd) + 255) & ~255ull;
-    W.bpart = (Bwd *)p;
+    W.fpart = (SplFwd *)p; p += fbytes;
+    W.bpart = (SplBwd *)p;
     return BPE_OK;
 }
 
-// host text (n bytes of UTF-8) -> W.bytes on the device and W.flag[i] = 1 at every chunk start
-static int split_flags(bpe_handle *h, const uint8_t *bytes, u64 n, SplitWork &W) {
+// host text (n bytes of UTF-8) -> W.bytes on the device; then either W.flag[i] = 1 at every chunk start
+// (tokens == nullptr) or tokens[i] = byte | chunk mark
+static int split_run(bpe_handle *h, const uint8_t *bytes, u64 n, SplitWork &W, u32 *tokens) {
     if (!h->d_cls) return fail(h, BPE_ERR_STATE, "call bpe_gpt4_tables first");
     if (n == 0) return BPE_OK;
     if (n >= 0xfffffff0ull) return fail(h, BPE_ERR_ARG, "device split handles at most 4 GiB - 16 per call");
@@ -62,16 +57,15 @@ static int split_flags(bpe_handle *h, const uint8_t *bytes, u64 n, SplitWork &W)
     CU(cudaMemcpyAsync(W.bytes, bytes, n, cudaMemcpyHostToDevice, h->stream));
     h->tm.h2d_bytes = n;
     const u32 ntiles = (u32)((n + SP_TILE - 1) / SP_TILE);
-    const int g = h->sms * 8;
     cudaEvent_t e0 = nullptr, e1 = nullptr;
     if (h->opt_kernel_timing) { cudaEventCreate(&e0); cudaEventCreate(&e1); cudaEventRecord(e0, h->stream); }
-    k_split_classify<<<g, 256, 0, h->stream>>>(W.bytes, n, h->d_cls, W.meta);
+    k_split_classify<<<h->sms * 8, 256, 0, h->stream>>>(W.bytes, n, h->d_cls, W.meta);
     k_split_reduce<<<ntiles, SP_THREADS, 0, h->stream>>>(W.meta, n, W.fpart, W.bpart);
     k_split_scan_parts<<<1, 1024, 0, h->stream>>>(W.fpart, W.bpart, ntiles);
-    k_split_down<<<ntiles, SP_THREADS, 0, h->stream>>>(W.meta, n, W.fpart, W.bpart, W.rs, W.nl, W.cnt, W.re, W.nnl);
-    k_split_rules<<<g, 256, 0, h->stream>>>(W.bytes, n, W.meta, h->d_contr, W.rs, W.nl, W.cnt, W.re, W.nnl, W.flag);
-    h->tm.kernel_launches += 5;
-    if (e0) {   // BPE_OPT_KERNEL_TIMING: device time of the five split kernels -> bpe_timing.init_ms
+    if (tokens) k_split_apply<true><<<ntiles, SP_THREADS, 0, h->stream>>>(W.bytes, W.meta, n, h->d_contr, W.fpart, W.bpart, nullptr, tokens);
+    else k_split_apply<false><<<ntiles, SP_THREADS, 0, h->stream>>>(W.bytes, W.meta, n, h->d_contr, W.fpart, W.bpart, W.flag, nullptr);
+    h->tm.kernel_launches += 4;
+    if (e0) {   // BPE_OPT_KERNEL_TIMING: device time of the four split kernels -> bpe_timing.init_ms
         cudaEventRecord(e1, h->stream); cudaEventSynchronize(e1);
         float ms = 0; cudaEventElapsedTime(&ms, e0, e1); h->tm.init_ms = ms;
         cudaEventDestroy(e0); cudaEventDestroy(e1);
@@ -110,7 +104,7 @@ extern "C" int bpe_split_gpt4(bpe_handle *h, const uint8_t *bytes, uint64_t n, u
     h->tm.h2d_bytes = 0; h->tm.d2h_bytes = 0; h->tm.kernel_launches = 0;
     if (n == 0) return BPE_OK;
     SplitWork W;
-    int rc = split_flags(h, bytes, n, W);
+    int rc = split_run(h, bytes, n, W, nullptr);
     u64 *d_offs = nullptr;
     if (!rc && cudaMalloc(&d_offs, n * 8) != cudaSuccess) rc = fail(h, BPE_ERR_CUDA, "cudaMalloc offsets");
     if (!rc) rc = flags_to_offsets(h, W.flag, n, d_offs, n_chunks);
@@ -141,11 +135,14 @@ extern "C" int bpe_load_text_gpt4(bpe_handle *h, const uint8_t *bytes, uint64_t 
     u64 chunks = 0;
     if (n) {
         SplitWork W;
-        rc = split_flags(h, bytes, n, W);
-        if (rc) return rc;
-        k_widen_marked<<<h->sms * 8, 256, 0, h->stream>>>(W.bytes, W.flag, h->buf[0], n);
-        h->tm.kernel_launches += 1;
-        if (n_chunks) {   // only counted on request (one extra pass over the flags)
+        if (!n_chunks) {   // the usual case: token words with their chunk marks straight from the rule kernel
+            rc = split_run(h, bytes, n, W, h->buf[0]);
+            if (rc) return rc;
+        } else {           // chunk count requested: flags, one counting pass over them, then widen + mark
+            rc = split_run(h, bytes, n, W, nullptr);
+            if (rc) return rc;
+            k_widen_marked<<<h->sms * 8, 256, 0, h->stream>>>(W.bytes, W.flag, h->buf[0], n);
+            h->tm.kernel_launches += 1;
             const u32 ntiles = (u32)((n + SP_TILE - 1) / SP_TILE);
             u32 *part = nullptr; u64 *excl = nullptr, *d_total = nullptr;
             if (cudaMalloc(&part, (size_t)ntiles * 4) == cudaSuccess && cudaMalloc(&excl, (size_t)ntiles * 8) == cudaSuccess &&

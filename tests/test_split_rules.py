@@ -74,3 +74,31 @@ def test_local_formulation_corpus(taylorswift):
     from oracle.split_rules_local import split as split_local
     text = taylorswift[:60000]
     assert split_local(text) == GPT4.findall(text)
+
+
+def test_product_rule_code_on_cpu(taylorswift):
+    """minbpe_b200/csrc/split_logic.h — the scan operators and the chunk-start rule the CUDA splitter is built
+    from — compiled for the CPU (oracle/split_harness.cpp) with the scans evaluated tile by tile like the
+    kernels do, against `regex` (byte offsets of every chunk)."""
+    import numpy as np
+
+    import oracle
+    from minbpe_b200.unicode_tables import tables
+    cls, contr = tables()
+
+    def check_bytes(text, tiles):
+        data, offs = oracle.split_to_stream(text, GPT4)
+        for tile in tiles:
+            got = oracle.split_logic_offsets(data.tobytes(), cls, contr, tile)
+            assert np.array_equal(got, offs), (text[:80], tile)
+
+    for t in CASES:
+        if t:
+            check_bytes(t, (0, 1, 3, 7, 64))
+    rnd = random.Random(4242)
+    alphabet = list("ab'sSdDmMtTlLvVeErR 12\t\n\r!.,' 　é日ſ½") + ["  ", "\n\n", "'ll", "'ve", " '", "K", "\U0001f600"]
+    for _ in range(4000):
+        check_bytes("".join(rnd.choice(alphabet) for _ in range(rnd.randint(1, 24))), (0, rnd.randint(1, 9)))
+    check_bytes(taylorswift, (0, 5, 2048, 4096))
+    from minbpe_b200.synth import generate
+    check_bytes(generate(1337, 2 << 20).tobytes().decode("utf-8"), (4096,))
