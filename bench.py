@@ -38,15 +38,32 @@ sys.path.insert(0, ROOT)
 GPT4 = r"""'(?i:[sdmt]|ll|ve|re)|[^\r\n\p{L}\p{N}]?+\p{L}+|\p{N}{1,3}| ?[^\s\p{L}\p{N}]++[\r\n]*|\s*[\r\n]|\s+(?!\S)|\s+"""
 
 
+def kernel_source_sha():
+    """sha256 over the sources of the dominant kernel (k_merge_seg): a committed ncu capture is only quoted
+    while it describes the kernel that is being timed."""
+    import hashlib
+    h = hashlib.sha256()
+    for f in ("k_merge_seg.cuh", "k_merge.cuh", "common.cuh", "k_seg.cuh"):
+        h.update(open(os.path.join(ROOT, "minbpe_b200", "csrc", f), "rb").read())
+    return h.hexdigest()[:16]
+
+
 def ncu_traffic():
     """DRAM bytes of one profiled launch of the dominant kernel (ncu --set full, committed under profiles/);
-    null when no capture of the current kernel is on record."""
+    null when no capture of the CURRENT kernel source is on record (the capture carries the source hash)."""
     p = os.path.join(ROOT, "profiles", "ncu_traffic.json")
     try:
         d = json.load(open(p))
-        return d["dram_bytes"], d
     except Exception:  # noqa: BLE001
         return None, None
+    sha = kernel_source_sha()
+    if d.get("kernel_source_sha") != sha:
+        return None, {"stale": True, "capture_sha": d.get("kernel_source_sha"), "current_sha": sha,
+                      "note": "profiles/ncu_traffic.json was captured from another version of the kernel; re-run tools/ncu_traffic.sh"}
+    return d["dram_bytes"], d
+
+
+from minbpe_b200.presplit import host_cores  # noqa: E402  (affinity mask capped by the cgroup CPU quota)
 
 
 def measured_peak():
@@ -172,6 +189,27 @@ def cpu_port_run(raw, offs, sample_bytes, steps, warmup=0):
     return cut, done, dt
 
 
+def python_reference_run(raw, nbytes=1 << 20, merges=8):
+    """The UNMODIFIED pure-Python reference (vendored to oracle/_ref by oracle/make_ref.py) on the first `nbytes`
+    of the corpus: RegexTokenizer.train(text, 256 + merges) — regex.py:36-70 with its own regex split.  One core
+    (the reference is single-threaded).  None when the vendored copy is absent."""
+    from oracle import make_ref
+    ref = make_ref.load()
+    if ref is None:
+        return None
+    cut = nbytes
+    while cut < raw.size and (raw[cut] & 0xC0) == 0x80:
+        cut += 1
+    text = raw[:cut].tobytes().decode("utf-8")
+    tok = ref.RegexTokenizer()
+    t0 = time.perf_counter()
+    tok.train(text, 256 + merges)
+    dt = time.perf_counter() - t0
+    return {"value": cut * merges / dt / 1e9, "unit": "GB/s", "cores": 1, "kind": "reference", "merges_per_s": merges / dt,
+            "seconds": dt, "first_pairs": [list(p) for p in list(tok.merges)[:4]],
+            "sample": f"karpathy/minbpe RegexTokenizer.train (pure Python, incl. its regex split) on the first {cut} bytes, {merges} merges"}
+
+
 def _ref_worker(args):
     seed, shard, nbytes, steps, warmup = args
     from minbpe_b200.presplit import chunk_offsets_1proc
@@ -183,39 +221,91 @@ def _ref_worker(args):
 
 
 def run_reference(args):
-    """--impl reference: the reference's CPU path (oracle port) on all host cores: one independent
-    replica of the merge loop per core, each on its own 16 MiB shard of synthetic text."""
+    """--impl reference: the reference's CPU path (oracle C port of base.py:13-41 + regex.py:49-63) on the host
+    cores this process may use (affinity mask capped by the cgroup quota): one independent replica of the merge
+    loop per core, each on its own 16 MiB shard of synthetic text.  Three passes, the median is reported, with the
+    parallel efficiency against one replica running alone; the pure-Python reference itself is timed beside it."""
     import multiprocessing as mp
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
     import oracle
     oracle.build()
-    cores = min(os.cpu_count() or 1, 64)
+    cores = min(host_cores(), 64)
     shard = 16 << 20
     steps = max(1, min(args.steps, 8))
     warm = min(args.warmup, 1)
     t0 = time.perf_counter()
+    solo = _ref_worker((args.seed, 0, shard, steps, warm))        # one replica alone: the per-core rate
+    solo_rate = solo[0] * solo[1] / solo[2] / 1e9
+    passes = []
     with mp.get_context("fork").Pool(cores) as pool:
-        res = pool.map(_ref_worker, [(args.seed, s, shard, steps, warm) for s in range(cores)])
+        for _ in range(3):
+            res = pool.map(_ref_worker, [(args.seed, s, shard, steps, warm) for s in range(cores)])
+            tmax = max(r[2] for r in res)
+            passes.append((sum(r[0] * r[1] for r in res) / tmax / 1e9, tmax, sum(r[1] for r in res) / tmax / cores))
     wall = time.perf_counter() - t0
-    tmax = max(r[2] for r in res)
-    total_bytes = sum(r[0] * r[1] for r in res)
-    value = total_bytes / tmax / 1e9
-    merges_per_s = sum(r[1] for r in res) / tmax / cores  # per replica
+    value, tmax, merges_per_s = sorted(passes)[1]
+    from minbpe_b200.synth import generate
+    pyref = python_reference_run(generate(args.seed, 2 << 20, threads=1))
     sample = (f"{cores} independent single-thread replicas of the oracle C port (bpe_oracle.c orc_train_step), each "
-              f"{steps} merge steps on its own 16 MiB synthetic shard (seed {args.seed}+1000*(shard+1)); time = slowest replica")
+              f"{steps} merge steps on its own 16 MiB synthetic shard (seed {args.seed}+1000*(shard+1)); time = slowest replica; "
+              f"median of 3 passes")
     line = {
         "impl": "reference", "metric": "train_loop_corpus_GBps", "value": value, "unit": "GB/s", "n_gpus": args.gpus,
         "steps": steps, "warmup": warm, "ms_per_step": tmax / steps * 1e3, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "int32", "data": "synthetic",
         "config": {"workload": "RegexTokenizer.train merge loop, GPT-4 split, synthetic UTF-8 (BASELINE configs[2] shape), "
-                               "bounded 16 MiB-per-core sample", "host_cores": cores, "wall_s": round(wall, 2)},
+                               "bounded 16 MiB-per-core sample", "host_cores": cores, "os_cpu_count": os.cpu_count(),
+                   "wall_s": round(wall, 2)},
         "merges_per_s": merges_per_s,
-        "cpu_baseline": {"value": value, "unit": "GB/s", "cores": cores, "kind": "port", "sample": sample},
+        "cpu_baseline": {"value": value, "unit": "GB/s", "cores": cores, "kind": "port", "sample": sample,
+                         "passes_GBps": [p[0] for p in passes], "one_replica_GBps": solo_rate,
+                         "parallel_efficiency": value / (solo_rate * cores), "python_reference": pyref},
         "e2e": {"value": value, "unit": "GB/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
     print(json.dumps(line), flush=True)
+
+
+def full_run(eng, raw, offs, merges, check=True):
+    """BASELINE configs[2] to completion: bpe_load_text_gpt4 + bpe_train(all merges) from the host text, then every
+    merge and count compared with the oracle's weighted loop over the distinct chunks of the host `regex` split
+    (oracle.c_dedup_chunks + c_train(weights): same dict as regex.py:51-54 builds, tests/test_oracle.py)."""
+    import torch
+    from minbpe_b200 import engine as E
+    eng.set_option(E.OPT_KERNEL_TIMING, 0)
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    eng.load_text_gpt4(raw)
+    t_load = time.perf_counter() - t0
+    pairs, counts, done = eng.train(merges)
+    torch.cuda.synchronize()
+    t_all = time.perf_counter() - t0
+    tm = eng.timing()
+    peak, _ = measured_peak()
+    t_loop = tm["loop_ms"] / 1e3
+    out = {"merges": int(done), "requested": int(merges), "seconds": t_all, "load_seconds": t_load, "loop_seconds": t_loop,
+           "init_ms": tm["init_ms"], "merges_per_s": done / t_loop, "corpus_GBps": raw.size * done / t_loop / 1e9,
+           "stream_GBps": 4.0 * tm["tokens_in"] / t_loop / 1e9,
+           "fused_bytes_frac_of_peak": (4.0 * tm["tokens_in"] + 4.0 * tm["tokens_out"]) / t_loop / 1e9 / peak,
+           "survey_8d_read_frac_of_peak": 8.0 * tm["tokens_in"] / t_loop / 1e9 / peak,
+           "table_slots": int(tm["table_slots"]), "table_used": int(tm["table_used"]),
+           "same_pairs": int(sum(1 for a, b in pairs.tolist() if a == b)), "final_tokens": int(eng.stream_len()),
+           "gpu_launches": int(tm["kernel_launches"]), "end_to_end_corpus_MBps": raw.size / t_all / 1e6}
+    if check:
+        import oracle
+        t0 = time.perf_counter()
+        ub, uo, uw = oracle.c_dedup_chunks(raw, offs)
+        wp, wc, wn = oracle.c_train(ub.astype(np.int32), uo, merges, weights=uw)
+        out["oracle_seconds"] = time.perf_counter() - t0
+        out["distinct_chunks"] = int(uo.size)
+        out["parity_all_merges"] = bool(wn == done and np.array_equal(pairs, wp) and np.array_equal(counts, wc))
+        if not out["parity_all_merges"]:
+            k = min(len(pairs), len(wp))
+            bad = np.flatnonzero((pairs[:k] != wp[:k]).any(axis=1) | (counts[:k] != wc[:k]))
+            out["first_mismatch"] = int(bad[0]) if bad.size else k
+    eng.set_option(E.OPT_KERNEL_TIMING, 1)
+    return out, pairs
 
 
 # ---------------------------------------------------------------------------------------------
@@ -245,7 +335,7 @@ def run_ours(args):
         cpu = {"value": cut * done / dt / 1e9, "unit": "GB/s", "cores": 1, "kind": "port",
                "sample": f"first {cut} bytes of the same corpus, {done} merge steps of oracle/bpe_oracle.c orc_train_step "
                          f"(C restatement of base.py:13-41 + regex.py:49-63), {dt:.1f} s, single thread",
-               "merges_per_s": done / dt}
+               "merges_per_s": done / dt, "python_reference": python_reference_run(raw)}
 
     from minbpe_b200 import engine as E
     torch.cuda.set_device(local)
@@ -295,6 +385,9 @@ def run_ours(args):
     peak, peak_src = measured_peak()
     k_ms = tm["merge_kernel_ms"] / K
     achieved = (4.0 * n_in + 4.0 * n_out) / K / (k_ms / 1e3) / 1e9
+    full = None
+    if args.full_merges > 0:
+        full, _ = full_run(eng, raw, offs, args.full_merges, check=not args.no_cpu_baseline)
     line = {
         "metric": "train_loop_corpus_GBps", "value": value, "unit": "GB/s", "n_gpus": 1, "steps": K, "warmup": W,
         "ms_per_step": t_loop / K * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
@@ -316,6 +409,7 @@ def run_ours(args):
                      "peak_source": peak_src, "bytes_per_launch": (4.0 * n_in + 4.0 * n_out) / K, "ms_per_launch": k_ms,
                      "loop_frac_in_kernel": tm["merge_kernel_ms"] / tm["loop_ms"]},
         "cpu_baseline": cpu,
+        "full_run": full,
         "e2e": {"value": size * (W + K) / t_e2e / 1e9, "unit": "GB/s", "h2d_bytes_per_step": h2d / (W + K),
                 "d2h_bytes_per_step": d2h / (W + K), "seconds": t_e2e, "merges": W + K,
                 "load_seconds": t_load, "runs_seconds": [r[0] for r in e2e_runs], "host_buffer": "pinned (cudaHostRegister)" if pinned else "pageable",
@@ -396,6 +490,9 @@ def main():
     ap.add_argument("--size-mib", type=int, default=1024, help="corpus bytes per GPU (MiB)")
     ap.add_argument("--seed", type=int, default=1337)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--full-merges", type=int, default=32512,
+                    help="N=1: also run the whole train() loop (this many merges, configs[2] = 32512) from the host text "
+                         "and compare every merge with the oracle; 0 = skip")
     ap.add_argument("--extras", action="store_true", help="side measurements (cfg2 wall time, encode throughput)")
     args = ap.parse_args()
     if args.warmup < 3 and args.impl == "ours":

@@ -43,7 +43,9 @@ struct bpe_handle {
     bool table_valid = false;  // table == get_stats(current stream)
     u64 *desc = nullptr; u64 desc_cap = 0;
     Edge *edge[2] = {nullptr, nullptr}; u64 *seg_offs = nullptr; u64 seg_cap = 0;  // segmented stream metadata
-    ull *delta = nullptr; u32 V = 0;
+    ull *delta = nullptr; u32 V = 0;   // V = layout of the delta vector the kernels index (L[0,V) R[V,2V) ZZ[2V])
+    u32 delta_cap = 0;                 // vocabulary capacity of the OWNED buffer `delta` (step mode uses the caller's)
+    u32 max_id = 255;                  // largest id in the loaded stream (bpe_load_ids); byte streams: 255
     ull *dense = nullptr;
     u32 *d_err = nullptr;
     int *log_pairs = nullptr; long long *log_counts = nullptr; int log_cap = 0;
@@ -142,7 +144,7 @@ extern "C" int bpe_create(int device, bpe_handle **out) {
     if ((e = cudaMalloc(&h->ctl, sizeof(Ctl))) != cudaSuccess) return bail("cudaMalloc ctl", e);
     if ((e = cudaMallocHost(&h->h_ctl, sizeof(Ctl))) != cudaSuccess) return bail("cudaMallocHost", e);
     if ((e = cudaMalloc(&h->dense, 65536 * 8)) != cudaSuccess) return bail("cudaMalloc dense", e);
-    if ((e = cudaMalloc(&h->d_err, 4)) != cudaSuccess) return bail("cudaMalloc err", e);
+    if ((e = cudaMalloc(&h->d_err, 8)) != cudaSuccess) return bail("cudaMalloc err", e);   // [0] error flag, [1] max id seen by k_copy_ids
     int occ = 1;
     int occ_same = 1;
     cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_same, k_merge<true>, MG_THREADS, 0);
@@ -351,7 +353,7 @@ extern "C" int bpe_load_stream(bpe_handle *h, const uint8_t *bytes, uint64_t n, 
     if ((rc = mark_chunks(h, h->buf[0], chunk_offsets, n_chunks, n))) return rc;
     if ((rc = reset_ctl_for_stream(h, n))) return rc;
     if ((rc = build_edges(h, n))) return rc;
-    h->loaded = true; h->bytes_only = true;
+    h->loaded = true; h->bytes_only = true; h->max_id = 255;
     return BPE_OK;
 }
 
@@ -366,15 +368,17 @@ extern "C" int bpe_load_ids(bpe_handle *h, const int32_t *ids, uint64_t n, const
     h->tm.h2d_bytes = 0;
     h->loaded = false; h->table_valid = false;
     if ((rc = ensure_stream_capacity(h, n))) return rc;
+    h->max_id = 0;
     if (n) {
         // stage through buf[1] (same size), then convert into buf[0]
         CU(cudaMemcpyAsync(h->buf[1], ids, n * 4, cudaMemcpyHostToDevice, h->stream));
-        CU(cudaMemsetAsync(h->d_err, 0, 4, h->stream));
+        CU(cudaMemsetAsync(h->d_err, 0, 8, h->stream));
         k_copy_ids<<<grid_for(n, 256, h->sms * 8), 256, 0, h->stream>>>((const int *)h->buf[1], h->buf[0], n, h->d_err);
-        u32 bad = 0;
-        CU(cudaMemcpyAsync(&bad, h->d_err, 4, cudaMemcpyDeviceToHost, h->stream));
+        u32 bad[2] = {0, 0};
+        CU(cudaMemcpyAsync(bad, h->d_err, 8, cudaMemcpyDeviceToHost, h->stream));
         CU(cudaStreamSynchronize(h->stream));
-        if (bad) return fail(h, BPE_ERR_ARG, "ids must be in [0, 2^31-1)");
+        if (bad[0]) return fail(h, BPE_ERR_ARG, "ids must be in [0, 2^31-1)");
+        h->max_id = bad[1];
         h->tm.h2d_bytes += n * 4;
     }
     if ((rc = mark_chunks(h, h->buf[0], chunk_offsets, n_chunks, n))) return rc;
@@ -501,6 +505,7 @@ extern "C" int bpe_merge(bpe_handle *h, int32_t a, int32_t b, int32_t idx, uint6
     if ((rc = pull_ctl(h))) return rc;
     h->table_valid = false;
     if (idx > 255) h->bytes_only = false;
+    h->max_id = std::max(h->max_id, (u32)idx);
     if (new_len) *new_len = h->h_ctl->n;
     return BPE_OK;
 }
@@ -517,12 +522,17 @@ static u64 auto_table_cap(bpe_handle *h, u64 n_unbounded_inserts) {
 }
 #define TABLE_MAX_LOAD 0.6
 
+// The owned delta vector must cover vocabulary capacity V; h->V (the layout every kernel indexes with) is
+// set to exactly V.  The capacity of the owned buffer is tracked separately: the step API points the
+// kernels at a caller's buffer and changes h->V without touching h->delta.
 static int ensure_delta(bpe_handle *h, u32 V) {
-    if (h->delta && h->V >= V) return BPE_OK;
-    if (h->delta) cudaFree(h->delta);
-    h->delta = nullptr; h->V = 0;
-    CU(cudaMalloc(&h->delta, (2ull * V + 1) * 8));
-    CU(cudaMemsetAsync(h->delta, 0, (2ull * V + 1) * 8, h->stream));
+    if (!h->delta || h->delta_cap < V) {
+        if (h->delta) cudaFree(h->delta);
+        h->delta = nullptr; h->delta_cap = 0;
+        CU(cudaMalloc(&h->delta, (2ull * V + 1) * 8));
+        h->delta_cap = V;
+    }
+    if (h->V != V) CU(cudaMemsetAsync(h->delta, 0, (2ull * h->delta_cap + 1) * 8, h->stream));   // layout changes: all zero again
     h->V = V;
     return BPE_OK;
 }
@@ -649,7 +659,10 @@ extern "C" int bpe_train(bpe_handle *h, int32_t num_merges, int32_t first_idx, i
     if (num_merges == 0) return BPE_OK;
     int rc = pull_ctl(h);
     if (rc) return rc;
-    const u32 V = (u32)first_idx + (u32)num_merges;
+    // the delta vector is indexed by the ids of a merge's neighbours: it must cover every id of the loaded
+    // stream (bpe_load_ids accepts any id < 2^31-1) as well as the ids this call creates
+    if ((u64)h->max_id + 1 >= 0x7fffffffull / 2) return fail(h, BPE_ERR_ARG, "bpe_train: ids of the loaded stream are too large for the dense delta vector");
+    const u32 V = std::max((u32)first_idx + (u32)num_merges, h->max_id + 1);
     if ((rc = ensure_delta(h, V))) return rc;
     if (h->log_cap < num_merges) {
         if (h->log_pairs) cudaFree(h->log_pairs);
@@ -719,6 +732,7 @@ extern "C" int bpe_train(bpe_handle *h, int32_t num_merges, int32_t first_idx, i
     *n_done = done_iters;
     h->table_valid = !h->opt_rescan;
     if (first_idx + done_iters > 256) h->bytes_only = false;
+    if (done_iters > 0) h->max_id = std::max(h->max_id, (u32)(first_idx + done_iters - 1));
     return BPE_OK;
 }
 

@@ -152,6 +152,10 @@ extern "C" int bpe_encode(bpe_handle *h, const uint8_t *bytes, uint64_t n, const
     if (n_merges < 0 || (n_merges && !merges)) return fail(h, BPE_ERR_ARG, "bad merges");
     if (n >= (1ull << 36)) return fail(h, BPE_ERR_ARG, "input too long");
     CU(cudaSetDevice(h->device));
+    {   // both encode paths index the text through these offsets: validate them once, up front
+        int rc0 = check_offsets(h, chunk_offsets, n_chunks, n);
+        if (rc0) return rc0;
+    }
     // encode works on its own scratch state so that a stream loaded for training is untouched
     bpe_handle *c = nullptr;
     int rc = bpe_create(h->device, &c);

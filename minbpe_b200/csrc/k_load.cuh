@@ -35,13 +35,17 @@ __global__ void k_set_flags(u32 *__restrict__ dst, const u64 *__restrict__ offs,
     }
 }
 
-// int32 ids -> token words (ids must be in [0, 2^31 - 1)); *err set on a negative id
+// int32 ids -> token words (ids must be in [0, 2^31 - 1)); err[0] set on a bad id, err[1] = largest id
 __global__ void k_copy_ids(const int *__restrict__ src, u32 *__restrict__ dst, u64 n, u32 *err) {
+    u32 mx = 0;
     for (u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (u64)gridDim.x * blockDim.x) {
         const int v = src[i];
-        if (v < 0 || v == 0x7fffffff) *err = 1;
+        if (v < 0 || v == 0x7fffffff) err[0] = 1;
+        else mx = max(mx, (u32)v);
         dst[i] = (u32)v & TOK_MASK;
     }
+    mx = __reduce_max_sync(0xffffffffu, mx);
+    if ((threadIdx.x & 31) == 0 && mx) atomicMax(&err[1], mx);
 }
 
 // token words -> int32 ids (chunk marks stripped)

@@ -33,7 +33,7 @@ def generate(seed, nbytes, threads=None, out=None, first_block=0):
     if out is None:
         out = np.empty(int(nbytes), dtype=np.uint8)
     assert out.dtype == np.uint8 and out.size == nbytes and out.flags["C_CONTIGUOUS"]
-    threads = threads or min(32, os.cpu_count() or 1)
+    threads = threads or min(32, len(os.sched_getaffinity(0)) if hasattr(os, 'sched_getaffinity') else (os.cpu_count() or 1))
     rc = _load().bpe_synth_generate_at(int(seed), int(first_block), out.ctypes.data, int(nbytes), int(threads))
     if rc != 0:
         raise RuntimeError(f"bpe_synth_generate failed: {rc}")

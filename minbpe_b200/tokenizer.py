@@ -286,7 +286,9 @@ class RegexTokenizer(Tokenizer):
     DEVICE_SPLIT_MIN_BYTES = 1 << 16
 
     def _device_split(self, nbytes):
-        return self.pattern == GPT4_SPLIT_PATTERN and nbytes >= self.DEVICE_SPLIT_MIN_BYTES
+        # the pattern that is actually used for splitting is compiled_pattern (regex.py:32,41,114), not the
+        # `pattern` string, which load() may have replaced
+        return self.compiled_pattern.pattern == GPT4_SPLIT_PATTERN and nbytes >= self.DEVICE_SPLIT_MIN_BYTES
 
     def train(self, text, vocab_size, verbose=False):
         assert vocab_size >= 256

@@ -326,3 +326,67 @@ int orc_train_step(int32_t *ids, uint8_t *start, uint64_t *n_io, int32_t idx,
     pm_free(&m);
     return rc;
 }
+
+/* ------------------------------------------------------------------------------------
+ * De-duplication of regex chunks (test-side accelerator for orc_train at corpus sizes the plain
+ * loop cannot reach; SURVEY.md §8c "Dedup note"): regex.py:51-54 visits the chunks in order and
+ * adds every chunk's pairs to ONE dict, so a chunk that occurs w times contributes w to each of its
+ * pairs at the position of its FIRST occurrence in the insertion order.  Training on the distinct
+ * chunks in first-occurrence order with weight w therefore gives the same dict (keys, order and
+ * counts) at every iteration — tests/test_oracle.py::test_dedup_weights_equal_plain pins
+ * orc_train(weights) == orc_train(plain) == the reference.
+ *   out_bytes / out_offs / out_weights : distinct chunks back to back, their starts, multiplicities
+ *   cap_chunks / cap_bytes             : capacities; ORC_ECAP when exceeded
+ * ---------------------------------------------------------------------------------- */
+static uint64_t hash_bytes(const uint8_t *p, uint64_t len) {
+    uint64_t h = 0x9e3779b97f4a7c15ULL ^ (len * 0xff51afd7ed558ccdULL);
+    uint64_t k = 0;
+    while (len >= 8) { memcpy(&k, p, 8); h = mix64(h ^ k); p += 8; len -= 8; }
+    if (len) { k = 0; memcpy(&k, p, len); h = mix64(h ^ k ^ (len << 56)); }
+    return h;
+}
+
+int orc_dedup_chunks(const uint8_t *bytes, uint64_t n, const uint64_t *offs, uint64_t n_chunks,
+                     uint8_t *out_bytes, uint64_t cap_bytes, uint64_t *out_offs, int64_t *out_weights,
+                     uint64_t cap_chunks, uint64_t *n_unique, uint64_t *n_out_bytes) {
+    uint64_t tcap = 1 << 16, used = 0, wbytes = 0;
+    uint64_t *tab = (uint64_t *)calloc(tcap, sizeof(uint64_t));   /* ordinal + 1, 0 = empty */
+    uint64_t *hashes = (uint64_t *)malloc(cap_chunks * sizeof(uint64_t));
+    if (!tab || !hashes) { free(tab); free(hashes); return ORC_ENOMEM; }
+    int rc = ORC_OK;
+    for (uint64_t c = 0; c < n_chunks; ++c) {
+        const uint64_t lo = offs[c], hi = (c + 1 < n_chunks) ? offs[c + 1] : n, len = hi - lo;
+        const uint64_t hv = hash_bytes(bytes + lo, len);
+        uint64_t s = hv & (tcap - 1);
+        int found = 0;
+        for (;;) {
+            const uint64_t o = tab[s];
+            if (!o) break;
+            if (hashes[o - 1] == hv) {
+                const uint64_t ulo = out_offs[o - 1], uhi = (o < used) ? out_offs[o] : wbytes;
+                if (uhi - ulo == len && memcmp(out_bytes + ulo, bytes + lo, len) == 0) { out_weights[o - 1] += 1; found = 1; break; }
+            }
+            s = (s + 1) & (tcap - 1);
+        }
+        if (found) continue;
+        if (used == cap_chunks || wbytes + len > cap_bytes) { rc = ORC_ECAP; break; }
+        memcpy(out_bytes + wbytes, bytes + lo, len);
+        out_offs[used] = wbytes; out_weights[used] = 1; hashes[used] = hv;
+        wbytes += len;
+        tab[s] = ++used;
+        if (used * 2 > tcap) {   /* grow */
+            const uint64_t ncap = tcap * 4;
+            uint64_t *nt = (uint64_t *)calloc(ncap, sizeof(uint64_t));
+            if (!nt) { rc = ORC_ENOMEM; break; }
+            for (uint64_t o = 0; o < used; ++o) {
+                uint64_t q = hashes[o] & (ncap - 1);
+                while (nt[q]) q = (q + 1) & (ncap - 1);
+                nt[q] = o + 1;
+            }
+            free(tab); tab = nt; tcap = ncap;
+        }
+    }
+    *n_unique = used; *n_out_bytes = wbytes;
+    free(tab); free(hashes);
+    return rc;
+}
