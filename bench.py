@@ -309,6 +309,325 @@ def full_run(eng, raw, offs, merges, check=True):
 
 
 # ---------------------------------------------------------------------------------------------
+# Shards of the synthetic corpus, the cfg4 strong-scaling leg, and the oracle check that works at 16 GiB
+def corpus_shard(seed, total_bytes, rank, world, threads):
+    """Bytes [lo, hi) of the `total_bytes` synthetic corpus of `seed` that belong to `rank`: equal parts whose ends
+    are moved to the next letter+space point (minbpe_b200.dist.shard_byte_range — a provable chunk boundary, so the
+    ranks' chunks together are exactly RegexTokenizer's split of the whole corpus).  Generated locally, block-wise."""
+    from minbpe_b200.dist import shard_byte_range
+    from minbpe_b200.synth import generate
+    MiB = 1 << 20
+
+    def fetch(a, b):
+        fb = a // MiB
+        buf = generate(seed, ((b + MiB - 1) // MiB - fb) * MiB, threads=1, first_block=fb)
+        return buf[a - fb * MiB: b - fb * MiB]
+    lo, hi = shard_byte_range(total_bytes, rank, world, fetch)
+    fb = lo // MiB
+    buf = generate(seed, ((hi + MiB - 1) // MiB - fb) * MiB, threads=threads, first_block=fb)
+    return buf[lo - fb * MiB: hi - fb * MiB], lo, hi
+
+
+def oracle_unique_chunks(eng, raw, workers):
+    """Distinct chunks of `raw` in first-occurrence order with multiplicities, for the weighted oracle loop
+    (oracle.c_dedup_chunks), at sizes where one pass is too slow: the text is cut into <= 1 GiB pieces at
+    letter+space points, each piece is split (device splitter, itself pinned against `regex` by the tests and by
+    the 1 GiB cross-check of every bench run) and de-duplicated on a host thread; the per-piece tables are merged
+    in text order.  -> (list of chunk bytes, weights)"""
+    from concurrent.futures import ThreadPoolExecutor
+    import oracle
+    from minbpe_b200.dist import first_safe_cut
+    piece = 1 << 30
+    cuts = [0]
+    while raw.size - cuts[-1] > piece:
+        lo = cuts[-1] + piece - (1 << 20)
+        p = first_safe_cut(raw[lo: lo + (1 << 20)])
+        assert p > 0
+        cuts.append(lo + p)
+    cuts.append(raw.size)
+
+    def dedup(a, b, offs):
+        ub, uo, uw = oracle.c_dedup_chunks(raw[a:b], offs, cap_chunks=1 << 22, cap_bytes=1 << 28)
+        ends = np.append(uo[1:], ub.size).astype(np.int64)
+        blob = ub.tobytes()
+        return [blob[int(x):int(y)] for x, y in zip(uo.astype(np.int64), ends)], uw
+
+    futs = []
+    with ThreadPoolExecutor(max(1, workers)) as pool:
+        for a, b in zip(cuts[:-1], cuts[1:]):
+            offs = eng.split_gpt4(raw[a:b])
+            futs.append(pool.submit(dedup, a, b, offs))
+        parts = [f.result() for f in futs]
+    return merge_unique(parts)
+
+
+def merge_unique(parts):
+    """Merge per-piece (chunks, weights) tables in text order, keeping first-occurrence order."""
+    index, chunks, weights = {}, [], []
+    for cs, ws in parts:
+        for c, w in zip(cs, np.asarray(ws).tolist()):
+            k = index.get(c)
+            if k is None:
+                index[c] = len(chunks)
+                chunks.append(c)
+                weights.append(w)
+            else:
+                weights[k] += w
+    return chunks, weights
+
+
+def oracle_train_unique(chunks, weights, merges):
+    import oracle
+    lens = np.fromiter(map(len, chunks), dtype=np.int64, count=len(chunks))
+    offs = np.zeros(len(chunks), dtype=np.uint64)
+    if len(chunks) > 1:
+        offs[1:] = np.cumsum(lens[:-1])
+    ids = np.frombuffer(b"".join(chunks), dtype=np.uint8).astype(np.int32)
+    return oracle.c_train(ids, offs, merges, weights=np.asarray(weights, dtype=np.int64))
+
+
+def merges_sha(pairs):
+    import hashlib
+    return hashlib.sha256(np.ascontiguousarray(pairs, dtype=np.int32).tobytes()).hexdigest()[:16]
+
+
+def strong_leg(args, eng, rank, world, local):
+    """BASELINE configs[3] (cfg4): RegexTokenizer.train on `strong_gib` GiB of synthetic UTF-8 (seed 1338) sharded by
+    byte range over the N GPUs, vocab 100000 (the per-merge statistics vector is the real 2*100000+1 counters).
+    STRONG scaling: the corpus is fixed, rank r holds part r of N.  Two timed windows of K merges of the same run —
+    dense early merges (W..W+K) and sparse later ones (S..S+K) — plus the sha256 of the merges so far (equal lines at
+    N = 1, 2, 4, 8 <=> identical merges) and a check of the first merges against the oracle's weighted loop over the
+    distinct chunks of the WHOLE corpus (gathered from all ranks).  N=1 runs the single-GPU device-driven loop
+    (bpe_train), N>1 the sharded loop with the NVLink exchange kernels."""
+    import torch
+    import torch.distributed as dist
+    from minbpe_b200 import engine as E
+    from minbpe_b200.dist import GpuStepEngine, ShardedTrainer
+    total = args.strong_gib << 30
+    vocab = args.strong_vocab
+    M = vocab - 256
+    K, W, S = args.steps, args.warmup, args.strong_sparse_at
+    threads = max(1, host_cores() // world)
+    t0 = time.time()
+    raw, lo, hi = corpus_shard(1338, total, rank, world, threads)
+    gen_s = time.time() - t0
+
+    def sync():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+            torch.cuda.synchronize()
+
+    def tmax(x):
+        if world == 1:
+            return x
+        t = torch.tensor([x], device="cuda", dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    sync()
+    t0 = time.perf_counter()
+    eng.load_text_gpt4(raw)
+    torch.cuda.synchronize()
+    load_s = tmax(time.perf_counter() - t0)
+    eng.set_option(E.OPT_KERNEL_TIMING, 0)
+    windows = {}
+    if world == 1:
+        eng.set_option(E.OPT_VOCAB_CAP, vocab)
+        done_total, all_pairs = 0, []
+
+        def advance(k, timed=None):
+            nonlocal done_total
+            if k <= 0:
+                return
+            torch.cuda.synchronize()
+            p, c, d = eng.train(k, first_idx=256 + done_total)
+            tm = eng.timing()
+            assert d == k, "corpus ran out of pairs"
+            all_pairs.append(p)
+            done_total += d
+            if timed:
+                windows[timed] = {"first_merge": done_total - k, "merges": k, "seconds": tm["loop_ms"] / 1e3,
+                                  "merges_per_s": k / (tm["loop_ms"] / 1e3), "tokens_in": int(tm["tokens_in"])}
+        advance(W)
+        advance(K, "dense")
+        advance(S - done_total)
+        advance(K, "sparse")
+        pairs = np.concatenate(all_pairs)
+        eng.set_option(E.OPT_VOCAB_CAP, 0)
+    else:
+        step = GpuStepEngine(eng, local)
+        tr = ShardedTrainer(step, rank, world, poll_every=16)
+        tr.prepare(M)
+
+        def window(k, name):
+            sync()
+            ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            first = tr.done
+            ev0.record(step.stream)
+            tr.run(k)
+            ev1.record(step.stream)
+            sync()
+            t = tmax(ev0.elapsed_time(ev1) / 1e3)
+            windows[name] = {"first_merge": first, "merges": tr.done - first, "seconds": t, "merges_per_s": (tr.done - first) / t}
+        tr.run(W)
+        window(K, "dense")
+        tr.run(S - tr.done)
+        window(K, "sparse")
+        pairs, _, n = tr.result()
+        pairs = pairs[:n]
+    # ---- parity: first P merges vs the oracle over the distinct chunks of the whole corpus ----
+    P = min(args.strong_check, len(pairs))
+    parity = None
+    if P > 0:
+        t0 = time.time()
+        chunks, weights = oracle_unique_chunks(eng, raw, threads)
+        if world > 1:
+            gathered = [None] * world
+            dist.all_gather_object(gathered, (chunks, weights))
+            if rank == 0:
+                chunks, weights = merge_unique(gathered)
+        if rank == 0:
+            wp, wc, wn = oracle_train_unique(chunks, weights, P)
+            parity = {"merges_checked": int(P), "equal": bool(wn == P and np.array_equal(pairs[:P], wp)),
+                      "distinct_chunks": len(chunks), "seconds": round(time.time() - t0, 1),
+                      "how": "oracle.c_train(weights) over the distinct chunks of the whole corpus (device split of every rank's "
+                             "shard, host de-duplication, tables merged in rank = text order)"}
+    if world > 1:
+        step.e.xchg_detach()
+        sync()
+    out = {"workload": f"BASELINE configs[3]: RegexTokenizer.train, {args.strong_gib} GiB synthetic UTF-8 (seed 1338), vocab {vocab}, "
+                       f"{world} GPU(s), contiguous byte-range shards cut at letter+space", "scaling": "strong",
+           "bytes_total": total, "bytes_this_rank": int(hi - lo), "vocab": vocab, "delta_vector_bytes": (2 * vocab + 1) * 8,
+           "exchange": "none (1 GPU)" if world == 1 else "NVLink peer memory kernels (k_xchg_cand on ties + k_xchg_apply), no NCCL per merge",
+           "nvlink_pull_bytes_per_merge_per_rank": 0 if world == 1 else (world - 1) * (2 * vocab + 1) * 8,
+           "generate_s": round(gen_s, 1), "load_seconds": load_s, "windows": windows,
+           "merges_sha16": merges_sha(pairs), "merges_in_sha": int(len(pairs)), "parity_vs_oracle": parity}
+    return out
+
+
+def run_sharded(args, rank, world, local):
+    """bench.py --gpus N>1 (one rank per GPU under torchrun).  Primary line: WEAK scaling of the cfg3-shaped loop, rank r
+    holding part r of one N * size_mib corpus (parts cut at letter+space: together exactly the RegexTokenizer split of
+    the whole corpus), per-merge exchanges by our NVLink peer-memory kernels.  `strong_cfg4` = strong_leg()."""
+    import torch
+    import torch.distributed as dist
+    from minbpe_b200 import engine as E
+    from minbpe_b200.dist import GpuStepEngine, ShardedTrainer
+    from minbpe_b200.presplit import chunk_offsets
+    size = args.size_mib << 20
+    K, W = args.steps, args.warmup
+    t0 = time.time()
+    threads = max(1, host_cores() // world)
+    raw, lo, hi = corpus_shard(args.seed, size * world, rank, world, threads)
+    offs = chunk_offsets(GPT4, raw, workers=threads)      # host `regex` split of the shard: cross-checks the device splitter
+    prep_s = time.time() - t0
+
+    torch.cuda.set_device(local)
+    dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    eng = E.Engine(local)
+    eng.set_option(E.OPT_KERNEL_TIMING, 1)
+    step = GpuStepEngine(eng, local)
+    sampler = None
+    if rank == 0:
+        sampler = ClockSampler(local)
+        sampler.start()
+
+    def sync_all():
+        torch.cuda.synchronize()
+        dist.barrier()
+        torch.cuda.synchronize()
+
+    # ---- e2e: host buffers -> merges through the C ABI (device split + sharded loop), wall clock, max over ranks ----
+    pinned = pin_host(raw)
+    eng.load_text_gpt4(raw)          # untimed warm-up of the load path
+    sync_all()
+    t0 = time.perf_counter()
+    eng.load_text_gpt4(raw)
+    h2d = eng.timing()["h2d_bytes"]
+    tr = ShardedTrainer(step, rank, world, poll_every=16)
+    tr.prepare(W + K)
+    tr.run()
+    pairs_e2e, _, n_e2e = tr.result()
+    sync_all()
+    t_e2e = torch.tensor([time.perf_counter() - t0], device="cuda")
+    dist.all_reduce(t_e2e, op=dist.ReduceOp.MAX)
+
+    # ---- device-resident: W warm-up merges, then exactly K timed; stream loaded from the HOST regex split ----
+    eng.load_stream(raw, offs)
+    tr = ShardedTrainer(step, rank, world, poll_every=16)
+    tr.prepare(W + K)
+    tr.run(W)
+    sync_all()
+    if sampler:
+        sampler.begin()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    eng.timing()
+    ev0.record(step.stream)
+    t0 = time.perf_counter()
+    tr.run(K)
+    ev1.record(step.stream)
+    sync_all()
+    wall = time.perf_counter() - t0
+    if sampler:
+        sampler.end()
+    clocks = sampler.stop() if sampler else None
+    t_loop = torch.tensor([ev0.elapsed_time(ev1) / 1e3], device="cuda")
+    dist.all_reduce(t_loop, op=dist.ReduceOp.MAX)
+    pairs, counts, n = tr.result()
+    tm = eng.timing()
+    ok = (n == W + K) and np.array_equal(pairs[: W + K], pairs_e2e)
+    merge_ms = torch.tensor([tm["merge_kernel_ms"] / max(n, 1)], device="cuda")   # CUDA events around the merge launches, all W+K steps
+    merge_all = [torch.zeros_like(merge_ms) for _ in range(world)]
+    dist.all_gather(merge_all, merge_ms)
+    strong = strong_leg(args, eng, rank, world, local) if args.strong_gib > 0 else None
+    if rank == 0:
+        t = float(t_loop.item())
+        peak, peak_src = measured_peak()
+        k_ms = t / K * 1e3
+        bytes_per_launch = 4.0 * (tm["tokens_in"] + tm["tokens_out"]) / max(n, 1)
+        V = 256 + W + K
+        line = {
+            "metric": "train_loop_corpus_GBps", "value": size * world * K / t / 1e9, "unit": "GB/s", "n_gpus": world,
+            "steps": K, "warmup": W, "ms_per_step": t / K * 1e3, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "int32", "data": "synthetic",
+            "config": {"workload": f"RegexTokenizer.train merge loop (GPT-4 split), {args.size_mib} MiB synthetic UTF-8 per GPU "
+                                   f"(seed {args.seed}): rank r = part r of one {args.size_mib * world} MiB corpus, parts cut at "
+                                   f"letter+space (a provable chunk boundary), merge steps {W}..{W + K - 1}; per merge: candidate push on "
+                                   f"ties + delta pull/sum fused with the table update, over NVLink peer memory (k_xchg.cuh), no NCCL call",
+                       "parallelism": f"shard{world}", "prep_s": round(prep_s, 1), "consistent": bool(ok),
+                       "shard_bytes_rank0": int(hi - lo),
+                       "l2": "per-GPU stream >> 126 MB L2, re-read from HBM every step",
+                       "timing": "CUDA events on the shared stream, max over ranks, barrier + synchronize on both sides"},
+            "merges_per_s": K / t, "wall_ms_per_step": wall / K * 1e3,
+            "gpu_launches": int(tm["kernel_launches"]),
+            "clocks": clocks,
+            "phases_ms": {"step": k_ms, "merge_kernels_per_rank": [float(x.item()) for x in merge_all],
+                          "select_exchange_apply": k_ms - max(float(x.item()) for x in merge_all),
+                          "how": "merge = CUDA events around the merge launches (every rank); the rest of the step = arg-max, tie filter, "
+                                 "first-occurrence scan, candidate exchange, delta exchange + table update, and waiting for the slowest rank"},
+            "exchange": {"kind": "NVLink peer memory (CUDA IPC), hand-written kernels", "delta_vector_bytes": (2 * V + 1) * 8,
+                         "nvlink_pull_bytes_per_merge_per_rank": (world - 1) * (2 * V + 1) * 8,
+                         "candidate_push_bytes_per_tie_per_rank": (world - 1) * 16},
+            "roofline": {"bound": "hbm", "kernel": "k_merge_seg (rank 0; rate over the whole step incl. exchanges)",
+                         "achieved": bytes_per_launch / (k_ms / 1e3) / 1e9, "peak": peak, "unit": "GB/s",
+                         "frac": bytes_per_launch / (k_ms / 1e3) / 1e9 / peak, "traffic": None, "peak_source": peak_src, "ms_per_launch": k_ms},
+            "cpu_baseline": None,
+            "strong_cfg4": strong,
+            "e2e": {"value": size * world * (W + K) / float(t_e2e.item()) / 1e9, "unit": "GB/s",
+                    "h2d_bytes_per_step": h2d / (W + K), "d2h_bytes_per_step": 16.0, "seconds": float(t_e2e.item()),
+                    "host_buffer": "pinned (cudaHostRegister)" if pinned else "pageable",
+                    "what": "per rank: bpe_load_text_gpt4(host shard text: H2D + device split) + sharded loop of W+K merges + merges D2H, wall clock, max over ranks"},
+            "first_pairs": pairs[W:W + 4].tolist(), "merges_sha16": merges_sha(pairs[: W + K]),
+        }
+        print(json.dumps(line), flush=True)
+    step.e.xchg_detach()
+    sync_all()
+    eng.close()
+    dist.destroy_process_group()
+
+
+# ---------------------------------------------------------------------------------------------
 def run_ours(args):
     import torch
     rank = int(os.environ.get("RANK", "0"))
@@ -321,8 +640,7 @@ def run_ours(args):
     K, W = args.steps, args.warmup
 
     if world > 1 or os.environ.get("BPE_BENCH_FORCE_SHARDED"):   # the env switch runs the sharded loop on one rank (tests)
-        from minbpe_b200.dist import bench_sharded
-        return bench_sharded(args, rank, world, local)
+        return run_sharded(args, rank, world, local)
 
     # host-side preparation, before CUDA is touched (the pre-split forks worker processes)
     raw, offs, prep = make_corpus(size, args.seed)
@@ -388,6 +706,9 @@ def run_ours(args):
     full = None
     if args.full_merges > 0:
         full, _ = full_run(eng, raw, offs, args.full_merges, check=not args.no_cpu_baseline)
+    strong = None
+    if args.strong_gib > 0:
+        strong = strong_leg(args, eng, 0, 1, local)
     line = {
         "metric": "train_loop_corpus_GBps", "value": value, "unit": "GB/s", "n_gpus": 1, "steps": K, "warmup": W,
         "ms_per_step": t_loop / K * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
@@ -410,6 +731,7 @@ def run_ours(args):
                      "loop_frac_in_kernel": tm["merge_kernel_ms"] / tm["loop_ms"]},
         "cpu_baseline": cpu,
         "full_run": full,
+        "strong_cfg4": strong,
         "e2e": {"value": size * (W + K) / t_e2e / 1e9, "unit": "GB/s", "h2d_bytes_per_step": h2d / (W + K),
                 "d2h_bytes_per_step": d2h / (W + K), "seconds": t_e2e, "merges": W + K,
                 "load_seconds": t_load, "runs_seconds": [r[0] for r in e2e_runs], "host_buffer": "pinned (cudaHostRegister)" if pinned else "pageable",
@@ -493,6 +815,12 @@ def main():
     ap.add_argument("--full-merges", type=int, default=32512,
                     help="N=1: also run the whole train() loop (this many merges, configs[2] = 32512) from the host text "
                          "and compare every merge with the oracle; 0 = skip")
+    ap.add_argument("--strong-gib", type=int, default=16,
+                    help="also run BASELINE configs[3] (strong scaling: this many GiB in total over the N GPUs, vocab "
+                         "--strong-vocab) and report it as strong_cfg4; 0 = skip")
+    ap.add_argument("--strong-vocab", type=int, default=100000)
+    ap.add_argument("--strong-sparse-at", type=int, default=1000, help="first merge of the second (sparse) timed window of the strong leg")
+    ap.add_argument("--strong-check", type=int, default=256, help="merges of the strong leg compared with the oracle (0 = none)")
     ap.add_argument("--extras", action="store_true", help="side measurements (cfg2 wall time, encode throughput)")
     args = ap.parse_args()
     if args.warmup < 3 and args.impl == "ours":

@@ -115,6 +115,19 @@ int bpe_encode(bpe_handle *h, const uint8_t *bytes, uint64_t n,
                const int32_t *merges, int32_t n_merges, const uint8_t *byte_perm,
                int32_t *out_ids, uint64_t out_cap, uint64_t *out_n);
 
+/* regex.py:111-121 (encode_ordinary) with the GPT-4 split done on the device as well: text bytes in, ids out; no
+ * chunk offsets exist anywhere (needs bpe_gpt4_tables).  Any length (pieces of 1 GiB cut at letter+space).
+ * Every DISTINCT chunk is encoded once (k_encode2.cuh): the memo table and the rank table stay with the handle while
+ * the caller keeps passing the same merges / byte_perm, so later calls and later pieces start warm.  bpe_encode with
+ * chunk_offsets (any split pattern, offsets from the host) runs the same kernels. */
+int bpe_encode_text_gpt4(bpe_handle *h, const uint8_t *bytes, uint64_t n, const int32_t *merges, int32_t n_merges,
+                         const uint8_t *byte_perm, int32_t *out_ids, uint64_t out_cap, uint64_t *out_n);
+/* Counters of the memoised encode: out[0] distinct chunks in the memo table, [1] ids in its pool; of the last call:
+ * [2] chunks newly added, [3] chunks encoded directly (no room in the table, or longer than 32 bytes), [4] of which
+ * long, [5] pieces, [6] pieces that took the general path, [7] device microseconds of the encode kernels
+ * (BPE_OPT_KERNEL_TIMING). */
+int bpe_encode_stats(bpe_handle *h, uint64_t *out /* [8] */);
+
 /* ---- the GPT-4 split pattern on the device (regex.py:19, used at regex.py:41 and :114) -------- */
 /* `re.findall(GPT4_SPLIT_PATTERN, text)` as scans + element-wise kernels (k_split.cuh; the rules are
  * pinned against the `regex` module by tests/test_split_rules.py).  The caller provides the Unicode
@@ -123,7 +136,8 @@ int bpe_encode(bpe_handle *h, const uint8_t *bytes, uint64_t n,
  * 4 apostrophe, 5 other} for cp < 0x110000, contr_table[cp] (cp < 0x3000) = bit0 (?i:[sdmt]),
  * bit1 (?i:l), bit2 (?i:v), bit3 (?i:e), bit4 (?i:r). */
 int bpe_gpt4_tables(bpe_handle *h, const uint8_t *cls_table, const uint8_t *contr_table);
-/* Chunk start offsets (bytes) of valid UTF-8 `bytes` under the GPT-4 pattern. */
+/* Chunk start offsets (bytes) of valid UTF-8 `bytes` under the GPT-4 pattern.  Any length: texts beyond 1 GiB are
+ * processed in pieces cut at provable chunk boundaries (ASCII letter followed by U+0020). */
 int bpe_split_gpt4(bpe_handle *h, const uint8_t *bytes, uint64_t n, uint64_t *out_offsets, uint64_t cap,
                    uint64_t *n_chunks);
 /* regex.py:41-44 without the host: upload + split + widen; same stream as
@@ -170,6 +184,25 @@ int bpe_decode(bpe_handle *h, const int32_t *ids, uint64_t n_ids, const uint8_t 
                const uint64_t *vocab_start, const uint32_t *vocab_len, int32_t V, uint8_t *out, uint64_t cap,
                uint64_t *out_n, int64_t *bad_index);
 
+/* ---- the same loop with the per-merge exchanges over NVLink peer memory (k_xchg.cuh) ------------- */
+/* Replaces the two host-issued collectives per merge (MIN over the candidate, SUM over the delta vector) by
+ * kernels that push / pull through CUDA-IPC-mapped peer memory: a tie pushes one candidate word to every
+ * peer (a unique arg-max needs no exchange: the table is replicated), and the delta all-reduce is fused
+ * with the table update (every rank pulls and sums the N local vectors while applying them).  No host call
+ * per merge.  Sequence:
+ *     bpe_xchg_create (every rank)  ->  all-gather the 64-byte handles (host)  ->  bpe_xchg_attach
+ *     bpe_step_begin, all-reduce of the 65536-bin histogram (once), bpe_step_table         (as above)
+ *     bpe_step_fused(n) ... bpe_step_poll ... bpe_step_result
+ * vocab_cap must equal first_idx + num_merges of bpe_step_table.  world <= 16, one process per GPU on one
+ * NVLink box (peer access required).  world == 1 works without peers (tests). */
+int bpe_xchg_create(bpe_handle *h, int32_t world, int32_t rank, int32_t vocab_cap, uint8_t *ipc_handle_out /* [64] */);
+int bpe_xchg_attach(bpe_handle *h, const uint8_t *all_handles /* [world][64], own slot ignored */);
+/* Unmap the peers' blocks (before any rank re-creates or destroys its own: detach everywhere, synchronise the
+ * ranks, then bpe_xchg_create / bpe_destroy). */
+int bpe_xchg_detach(bpe_handle *h);
+/* regex.py:49-63, n_iters iterations enqueued on the handle's stream; returns at once. */
+int bpe_step_fused(bpe_handle *h, int32_t n_iters);
+
 /* ---- measurement --------------------------------------------------------------------------- */
 
 typedef struct {
@@ -195,6 +228,12 @@ int bpe_get_timing(bpe_handle *h, bpe_timing *out);
                                    instead of maintaining it incrementally (verification) */
 #define BPE_OPT_BATCH 3         /* max merge iterations enqueued per host synchronisation */
 #define BPE_OPT_TABLE_LOG2 4    /* log2 of the pair-count table capacity (0 = automatic) */
+#define BPE_OPT_VOCAB_CAP 6     /* bpe_train: size the per-merge statistics delta vector for at least this vocabulary
+                                   (a training run split over several bpe_train calls then keeps one layout; bench: the
+                                   vocab-100000 configuration timed over a window of its merges) */
+#define BPE_OPT_ENC_MEMO_LOG2 7 /* test hook: log2 of the slots of the encode memo table (0 = default 22); drops the current table */
+#define BPE_OPT_SPLIT_PIECE 5   /* test hook: bytes per piece of the device splitter (0 = default 1 GiB); texts longer than
+                                   a piece are cut where a letter is followed by U+0020 (process-wide) */
 int bpe_set_option(bpe_handle *h, int opt, int64_t value);
 
 /* Test hook: live entries (count > 0) of the incrementally maintained pair-count table, in no

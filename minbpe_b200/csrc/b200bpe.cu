@@ -20,11 +20,16 @@
 #include "k_encode.cuh"
 #include "k_split.cuh"
 #include "k_decode.cuh"
+#include "k_xchg.cuh"
+#include "k_encode2.cuh"
 
 #define BPE_ABI_VERSION 1
 
+struct EncState;
 struct bpe_handle {
     int device = 0;
+    EncState *enc = nullptr;          // memoised chunk encode (encode2_host.inl): rank table, memo, id pool, scratch
+    bpe_handle *enc_scratch = nullptr;   // general encode path (encode_host.inl) works on its own stream buffers
     int sms = 0;
     cudaStream_t stream = nullptr;       // the stream every kernel of this handle runs on
     cudaStream_t own_stream = nullptr;   // created by bpe_create; `stream` may point at a caller's stream instead
@@ -51,6 +56,10 @@ struct bpe_handle {
     int *log_pairs = nullptr; long long *log_counts = nullptr; int log_cap = 0;
     Best *partials = nullptr;
     unsigned char *d_cls = nullptr, *d_contr = nullptr;   // code-point class / contraction tables of the GPT-4 splitter
+    // sharded loop over NVLink peer memory (k_xchg.cuh): the rank's exchange block and its peers' mappings
+    unsigned char *xchg = nullptr; u64 xchg_bytes = 0, xchg_stride = 0; u32 xchg_V = 0;
+    XArgs xargs = {};
+    bool xchg_attached = false;
     u32 *d_present = nullptr;   // sharded loop: bitmap of pair hashes that have occurred in this shard (k_stats.cuh)
     unsigned char *split_slab = nullptr; u64 split_cap = 0;   // working set of the splitter, kept between calls (split_host.inl)
     int argmax_grid = 0, merge_grid = 0, merge_grid_same = 0, merge_grid_seg = 0, ff_grid = 0;
@@ -58,6 +67,8 @@ struct bpe_handle {
     // options
     int step_poll_every = 16;
     int opt_kernel_timing = 0, opt_rescan = 0, opt_batch = 256, opt_table_log2 = 0;
+    int opt_memo_log2 = 0;   // BPE_OPT_ENC_MEMO_LOG2 (test hook): log2 slots of the encode memo table, 0 = default
+    u32 opt_vocab_cap = 0;   // BPE_OPT_VOCAB_CAP: lower bound of the delta-vector layout V used by bpe_train
 
     bpe_timing tm = {};
     std::vector<cudaEvent_t> ev_pool;  // per-launch timing of the fused merge kernel (BPE_OPT_KERNEL_TIMING)
@@ -65,6 +76,9 @@ struct bpe_handle {
 };
 
 static thread_local std::string g_create_err;
+static void xchg_release(bpe_handle *h);
+static void enc2_free(bpe_handle *h);
+static u64 g_split_piece_override = 0;   // BPE_OPT_SPLIT_PIECE (test hook): bytes per piece of the device splitter
 
 static int fail(bpe_handle *h, int code, const std::string &msg) {
     if (h) h->err = msg; else g_create_err = msg;
@@ -188,6 +202,9 @@ extern "C" int bpe_destroy(bpe_handle *h) {
     if (h->d_cls) cudaFree(h->d_cls);
     if (h->d_contr) cudaFree(h->d_contr);
     if (h->d_present) cudaFree(h->d_present);
+    xchg_release(h);
+    enc2_free(h);
+    if (h->enc_scratch) bpe_destroy(h->enc_scratch);
     if (h->split_slab) cudaFree(h->split_slab);
     if (h->ctl) cudaFree(h->ctl);
     if (h->h_ctl) cudaFreeHost(h->h_ctl);
@@ -205,6 +222,18 @@ extern "C" int bpe_set_option(bpe_handle *h, int opt, int64_t value) {
         case BPE_OPT_TABLE_LOG2:
             if (value != 0 && (value < 10 || value > 30)) return fail(h, BPE_ERR_ARG, "table log2 must be 0 or in [10,30]");
             h->opt_table_log2 = (int)value; break;
+        case BPE_OPT_VOCAB_CAP:
+            if (value < 0 || value >= 0x3fffffff) return fail(h, BPE_ERR_ARG, "vocabulary capacity out of range");
+            h->opt_vocab_cap = (u32)value; break;
+        case BPE_OPT_ENC_MEMO_LOG2:
+            if (value != 0 && (value < 6 || value > 28)) return fail(h, BPE_ERR_ARG, "memo log2 must be 0 or in [6,28]");
+            h->opt_memo_log2 = (int)value;
+            cudaSetDevice(h->device); cudaStreamSynchronize(h->stream);
+            enc2_free(h);   // re-created with the new size by the next encode call
+            break;
+        case BPE_OPT_SPLIT_PIECE:
+            if (value != 0 && value < 4096) return fail(h, BPE_ERR_ARG, "split piece must be 0 (default) or >= 4096 bytes");
+            g_split_piece_override = (u64)value; break;
         default: return fail(h, BPE_ERR_ARG, "unknown option");
     }
     return BPE_OK;
@@ -472,17 +501,19 @@ extern "C" int bpe_get_stats(bpe_handle *h, int32_t *pairs, int64_t *counts, uin
 // (which also refills every segment).  Every kernel gates itself on the device-resident pair, so
 // the whole sequence is enqueued unconditionally; `same` >= 0 lets the host skip the no-ops when
 // it knows the pair (single-step API).
-static void launch_merge(bpe_handle *h, ull *delta, int force, int same = -1) {
+static void launch_merge(bpe_handle *h, ull *delta, int force, int same = -1, bool use_xchg = false) {
+    const unsigned char *xbase = use_xchg ? h->xchg : nullptr;
     if (same != 1) {
         SegArgs S;
         S.ctl = h->ctl; S.buf0 = h->buf[0]; S.buf1 = h->buf[1]; S.e0 = h->edge[0]; S.e1 = h->edge[1];
-        S.delta = delta; S.V = h->V; S.force = force;
+        S.delta = delta; S.V = h->V; S.force = force; S.xbase = xbase; S.xstride = h->xchg_stride;
         k_merge_seg<<<h->merge_grid_seg, MS_THREADS, MS_SMEM_BYTES, h->stream>>>(S);
         h->tm.kernel_launches += 1;
     }
     if (same != 0) {
         MergeArgs A;
         A.ctl = h->ctl; A.buf0 = h->buf[0]; A.buf1 = h->buf[1]; A.desc = h->desc; A.delta = delta; A.V = h->V; A.force = force;
+        A.xbase = xbase; A.xstride = h->xchg_stride;
         enqueue_pack(h, force);
         k_merge<true><<<h->merge_grid_same, MG_THREADS, 0, h->stream>>>(A);
         h->tm.kernel_launches += 1;
@@ -589,11 +620,11 @@ static void drain_kernel_events(bpe_handle *h) {
     h->ev_used = 0;
 }
 
-static void timed_merge(bpe_handle *h, ull *delta) {
-    if (!h->opt_kernel_timing) { launch_merge(h, delta, 0); return; }
+static void timed_merge(bpe_handle *h, ull *delta, bool use_xchg = false) {
+    if (!h->opt_kernel_timing) { launch_merge(h, delta, 0, -1, use_xchg); return; }
     while ((int)h->ev_pool.size() < h->ev_used + 2) { cudaEvent_t e; cudaEventCreate(&e); h->ev_pool.push_back(e); }
     cudaEventRecord(h->ev_pool[h->ev_used], h->stream);
-    launch_merge(h, delta, 0);
+    launch_merge(h, delta, 0, -1, use_xchg);
     cudaEventRecord(h->ev_pool[h->ev_used + 1], h->stream);
     h->ev_used += 2;
 }
@@ -662,7 +693,7 @@ extern "C" int bpe_train(bpe_handle *h, int32_t num_merges, int32_t first_idx, i
     // the delta vector is indexed by the ids of a merge's neighbours: it must cover every id of the loaded
     // stream (bpe_load_ids accepts any id < 2^31-1) as well as the ids this call creates
     if ((u64)h->max_id + 1 >= 0x7fffffffull / 2) return fail(h, BPE_ERR_ARG, "bpe_train: ids of the loaded stream are too large for the dense delta vector");
-    const u32 V = std::max((u32)first_idx + (u32)num_merges, h->max_id + 1);
+    const u32 V = std::max(std::max((u32)first_idx + (u32)num_merges, h->max_id + 1), h->opt_vocab_cap);
     if ((rc = ensure_delta(h, V))) return rc;
     if (h->log_cap < num_merges) {
         if (h->log_pairs) cudaFree(h->log_pairs);
@@ -759,4 +790,5 @@ extern "C" int bpe_debug_table(bpe_handle *h, int32_t *pairs, int64_t *counts, u
 #include "encode_host.inl"
 #include "step_host.inl"
 #include "split_host.inl"
+#include "encode2_host.inl"
 #include "decode_host.inl"

@@ -112,6 +112,28 @@ struct __align__(32) Edge {
     u32 pad[2];
 };
 
+// ---- exchange block of the sharded loop (k_xchg.cuh): header + two delta vectors, in every rank's HBM ----
+#define XCHG_MAX_RANKS 16
+#define XCHG_HDR_BYTES 1024
+
+struct XHdr {
+    u32 seq;                          // exchange rounds completed (local copy; identical on every rank)
+    u32 exit_count;                   // blocks that left k_xchg_apply
+    u32 applied;                      // ctl->iter up to which the table has been updated (an iteration whose merge was
+                                      // gated off — done, max_iter — must not run an exchange round either)
+    u32 pad;
+    u64 dflag[XCHG_MAX_RANKS];        // dflag[r] = s+1: rank r's delta of round s is complete
+    u64 cflag[XCHG_MAX_RANKS];        // cflag[r] = s+1: rank r's candidate of round s is in cand[r]
+    long long cand[XCHG_MAX_RANKS];
+};
+static_assert(sizeof(XHdr) <= XCHG_HDR_BYTES, "exchange header must fit its slot");
+
+// the delta buffer the merge kernels of round XHdr.seq add into
+__device__ __forceinline__ ull *x_local_delta(const unsigned char *xbase, u64 delta_stride) {
+    const u32 s = reinterpret_cast<const XHdr *>(xbase)->seq;
+    return reinterpret_cast<ull *>(const_cast<unsigned char *>(xbase) + XCHG_HDR_BYTES + (u64)(s & 1u) * delta_stride);
+}
+
 // ---- small helpers -------------------------------------------------------------------------
 __device__ __forceinline__ u64 ld_volatile_u64(const u64 *p) {
     u64 v;

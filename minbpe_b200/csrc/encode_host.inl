@@ -144,33 +144,25 @@ static int encode_on(bpe_handle *h, const uint8_t *bytes, uint64_t n, const uint
     return rc;
 }
 
-extern "C" int bpe_encode(bpe_handle *h, const uint8_t *bytes, uint64_t n, const uint64_t *chunk_offsets,
-                          uint64_t n_chunks, const int32_t *merges, int32_t n_merges, const uint8_t *byte_perm,
-                          int32_t *out_ids, uint64_t out_cap, uint64_t *out_n) {
-    if (!h || !out_n) return BPE_ERR_ARG;
-    if (!bytes && n) return fail(h, BPE_ERR_ARG, "bytes is NULL");
-    if (n_merges < 0 || (n_merges && !merges)) return fail(h, BPE_ERR_ARG, "bad merges");
-    if (n >= (1ull << 36)) return fail(h, BPE_ERR_ARG, "input too long");
-    CU(cudaSetDevice(h->device));
-    {   // both encode paths index the text through these offsets: validate them once, up front
-        int rc0 = check_offsets(h, chunk_offsets, n_chunks, n);
-        if (rc0) return rc0;
+// The general path: thread per chunk / CTA per long chunk (k_encode.cuh), or rank-ordered rounds on the stream kernels
+// for one huge chunk (BasicTokenizer on a long text) or an oversized chunk.  Runs on a scratch handle that stays with
+// the parent (a stream loaded for training is not disturbed, and no handle is created per call).
+static int encode_general(bpe_handle *h, const uint8_t *bytes, uint64_t n, const uint64_t *chunk_offsets, uint64_t n_chunks,
+                          const int32_t *merges, int32_t n_merges, const uint8_t *byte_perm, int32_t *out_ids, uint64_t out_cap,
+                          uint64_t *out_n) {
+    if (!h->enc_scratch) {
+        int rc0 = bpe_create(h->device, &h->enc_scratch);
+        if (rc0) return fail(h, rc0, std::string("bpe_encode: ") + bpe_last_error(nullptr));
     }
-    // encode works on its own scratch state so that a stream loaded for training is untouched
-    bpe_handle *c = nullptr;
-    int rc = bpe_create(h->device, &c);
-    if (rc) return fail(h, rc, std::string("bpe_encode: ") + bpe_last_error(nullptr));
+    bpe_handle *c = h->enc_scratch;
     c->opt_batch = h->opt_batch; c->opt_table_log2 = h->opt_table_log2;
     int handled = 0;
-    rc = BPE_OK;
+    int rc = BPE_OK;
     if (n >= 1 && n_merges > 0 && (n_chunks >= 1 || n <= ENC_LONG_MAX))
         rc = encode_chunks_on(c, bytes, n, chunk_offsets, n_chunks, merges, n_merges, byte_perm, out_ids, out_cap, out_n, &handled);
-    // one huge chunk (BasicTokenizer on a long text) or an oversized chunk: rank-ordered rounds on the stream kernels
     if (!rc && !handled)
         rc = encode_on(c, bytes, n, chunk_offsets, n_chunks, merges, n_merges, byte_perm, out_ids, out_cap, out_n);
     if (rc) h->err = c->err;
-    h->tm.h2d_bytes = c->tm.h2d_bytes; h->tm.d2h_bytes = c->tm.d2h_bytes; h->tm.kernel_launches = c->tm.kernel_launches;
-    bpe_destroy(c);
+    h->tm.h2d_bytes += c->tm.h2d_bytes; h->tm.d2h_bytes += c->tm.d2h_bytes; h->tm.kernel_launches += c->tm.kernel_launches;
     return rc;
 }
-

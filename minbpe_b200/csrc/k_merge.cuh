@@ -90,6 +90,8 @@ struct MergeArgs {
     ull *delta;      // [0,V) L, [V,2V) R, [2V] ZZ; NULL = plain merge (no statistics)
     u32 V;
     int force;       // 1: run even if ctl->done / iter >= max_iter (single-step API)
+    const unsigned char *xbase;   // sharded loop: exchange block (k_xchg.cuh) whose current-parity delta vector replaces `delta`
+    u64 xstride;
 };
 
 // SAME = the kernel instance for pairs (a,a); both instances are launched back to back and the
@@ -116,6 +118,7 @@ __global__ void __launch_bounds__(MG_THREADS, SAME ? 2 : 3) k_merge(MergeArgs A)
     const u32 a = (u32)ctl->a, b = (u32)ctl->b, z = (u32)ctl->z;
     const u32 epoch = ctl->epoch;
     const u32 ntiles = (u32)((n + MG_TILE - 1) / MG_TILE);
+    ull *const delta = A.xbase ? x_local_delta(A.xbase, A.xstride) : A.delta;
 
     for (;;) {
         __syncthreads();
@@ -327,7 +330,7 @@ __global__ void __launch_bounds__(MG_THREADS, SAME ? 2 : 3) k_merge(MergeArgs A)
         }
 
         // ---- delta: statistics change caused by each merge start ------------------------------
-        if (A.delta) {
+        if (delta) {
 #pragma unroll
             for (int r = 0; r < MG_ROWS; ++r) {
                 if (mn[r]) {
@@ -341,14 +344,14 @@ __global__ void __launch_bounds__(MG_THREADS, SAME ? 2 : 3) k_merge(MergeArgs A)
                             // right-hand case) or p starts a chunk
                             if (p >= 1 && !(t[r][k] & TOK_FLAG) && !mark_bit(s_mnib, (long long)p - 2, ts)) {
                                 const u32 x = w[p - 1] & TOK_MASK;
-                                atomicAdd(&A.delta[x], 1ull);
+                                atomicAdd(&delta[x], 1ull);
                             }
                             // right neighbour y = token after the pair
                             if (p + 2 < n) {
                                 const u32 y = w[p + 2];
                                 if (!(y & TOK_FLAG)) {
-                                    if (mark_bit(s_mnib, (long long)p + 2, ts)) atomicAdd(&A.delta[2 * (u64)A.V], 1ull);
-                                    else atomicAdd(&A.delta[(u64)A.V + y], 1ull);
+                                    if (mark_bit(s_mnib, (long long)p + 2, ts)) atomicAdd(&delta[2 * (u64)A.V], 1ull);
+                                    else atomicAdd(&delta[(u64)A.V + y], 1ull);
                                 }
                             }
                         }

@@ -83,6 +83,8 @@ struct SegArgs {
     ull *delta;   // [0,V) L, [V,2V) R, [2V] ZZ; NULL = plain merge
     u32 V;
     int force;
+    const unsigned char *xbase;   // sharded loop: the rank's exchange block (k_xchg.cuh); the delta vector is then
+    u64 xstride;                  // the one of the current round's parity inside it, and `delta` is ignored
 };
 
 // one row (128 tokens, 4 per lane): merge starts m, kept tokens, replaced tokens written back to t[]
@@ -153,6 +155,7 @@ __global__ void __launch_bounds__(MS_THREADS, MS_MINBLOCKS) k_merge_seg(SegArgs 
     Edge *__restrict__ e_next = ctl->edge_cur ? A.e0 : A.e1;
     const u32 a = (u32)ctl->a, b = (u32)ctl->b, z = (u32)ctl->z;
     const u32 nseg = ctl->nseg;
+    ull *const delta = A.xbase ? x_local_delta(A.xbase, A.xstride) : A.delta;
 
     // this warp's private shared memory, as 32-bit shared-window byte addresses
     const u32 ws_a = smem_addr(s_warp + warp * MS_WARP_WORDS);   // [MS_STAGES][MS_SW] staging ring
@@ -272,13 +275,13 @@ __global__ void __launch_bounds__(MS_THREADS, MS_MINBLOCKS) k_merge_seg(SegArgs 
         }
 
         // ---- statistics delta of this segment's merge starts (reads the stage before it is rewritten) ----
-        if (A.delta) {
+        if (delta) {
             u32 mall = mn[0] | (mn[1] << 4) | (mn[2] << 8) | (mn[3] << 12);
 #pragma unroll 1
             while (mall) {   // one pass per merge start of this lane
                 const int bit = __ffs(mall) - 1;
                 mall &= mall - 1;
-                delta_one(la + (bit >> 2) * 512 + (bit & 3) * 4, a, b, A.V, s_dkey, s_dcnt, A.delta);
+                delta_one(la + (bit >> 2) * 512 + (bit & 3) * 4, a, b, A.V, s_dkey, s_dcnt, delta);
             }
         }
 
@@ -331,9 +334,9 @@ __global__ void __launch_bounds__(MS_THREADS, MS_MINBLOCKS) k_merge_seg(SegArgs 
 
     if (lane == 0 && drops) atomicAdd(s_drops, (ull)drops);
     __syncthreads();
-    if (A.delta)
+    if (delta)
         for (u32 i = tid; i < MS_DCACHE; i += MS_THREADS)
-            if (s_dkey[i] != 0xffffffffu && s_dcnt[i]) atomicAdd(&A.delta[s_dkey[i]], (ull)s_dcnt[i]);
+            if (s_dkey[i] != 0xffffffffu && s_dcnt[i]) atomicAdd(&delta[s_dkey[i]], (ull)s_dcnt[i]);
     // ---- exit: the last CTA out publishes the new stream length and flips the edge arrays ----
     if (tid == 0) {
         const ull cta_drops = *s_drops;

@@ -231,8 +231,9 @@ __global__ void __launch_bounds__(1024) k_flag_scan_parts(const u32 *__restrict_
     if (tid == 1023) *total = sm[1023];
 }
 
+// offs[] = text_base + position of every set flag (text_base: where this piece starts in the caller's text)
 __global__ void __launch_bounds__(SP_THREADS) k_flag_scatter(const unsigned char *__restrict__ flag, u64 n, const u64 *__restrict__ excl,
-                                                             u64 *__restrict__ offs) {
+                                                             u64 *__restrict__ offs, u64 text_base) {
     __shared__ u32 sm[SP_THREADS];
     const u32 tid = threadIdx.x;
     const u64 base = (u64)blockIdx.x * SP_TILE + (u64)tid * SP_ITEMS;
@@ -244,5 +245,5 @@ __global__ void __launch_bounds__(SP_THREADS) k_flag_scatter(const unsigned char
     for (int o = 1; o < SP_THREADS; o <<= 1) { const u32 v = tid >= (u32)o ? sm[tid - o] : 0; __syncthreads(); sm[tid] += v; __syncthreads(); }
     u64 dst = excl[blockIdx.x] + (sm[tid] - c);
 #pragma unroll
-    for (int k = 0; k < SP_ITEMS; ++k) if (base + k < n && flag[base + k]) offs[dst++] = base + k;
+    for (int k = 0; k < SP_ITEMS; ++k) if (base + k < n && flag[base + k]) offs[dst++] = text_base + base + k;
 }

@@ -87,6 +87,12 @@ extern "C" int bpe_step_table(bpe_handle *h, const uint64_t *dense_dev, int32_t 
     h->h_ctl->table_limit = (u64)(TABLE_MAX_LOAD * (double)cap);
     if ((rc = push_ctl(h))) return rc;
     h->table_valid = false;
+    h->tm.merge_kernel_ms = 0;
+    if (h->xchg) {   // ctl->iter restarts at 0; the buffer of the previous run's last round is still dirty (the caller has
+                     // synchronised the ranks, so no peer reads it any more)
+        CU(cudaMemsetAsync(h->xchg + offsetof(XHdr, applied), 0, 4, h->stream));
+        CU(cudaMemsetAsync(h->xchg + XCHG_HDR_BYTES, 0, 2 * h->xchg_stride, h->stream));
+    }
     h->step_poll_every = poll_every;
     h->tm.kernel_launches += 1;
     return step_headroom(h, poll_every);
@@ -139,6 +145,7 @@ extern "C" int bpe_step_poll(bpe_handle *h, int32_t *iters_done, int32_t *exhaus
     int rc = pull_ctl(h);
     if (rc) return rc;
     drain_kernel_events(h);
+    if (h->h_ctl->overflow == 2) return fail(h, BPE_ERR_INTERNAL, "NVLink exchange timed out waiting for a peer rank");
     if (h->h_ctl->overflow) return fail(h, BPE_ERR_INTERNAL, "pair table overflowed despite the head-room guarantee");
     *iters_done = (int32_t)h->h_ctl->iter;
     *exhausted = h->h_ctl->done != 0;
@@ -164,5 +171,99 @@ extern "C" int bpe_step_result(bpe_handle *h, int32_t *out_pairs, int64_t *out_c
         CU(cudaStreamSynchronize(h->stream));
     }
     if (h->h_ctl->first_idx + done > 256) h->bytes_only = false;
+    return BPE_OK;
+}
+
+
+// ================================================================================================
+// The same loop with the per-merge exchanges done by our own kernels over NVLink peer memory
+// (k_xchg.cuh) instead of two NCCL all-reduces issued by the host: no host call per merge at all.
+//
+//   bpe_xchg_create   allocate this rank's exchange block, return its CUDA IPC handle (64 bytes)
+//   (host: all-gather the handles of all ranks, e.g. torch.distributed)
+//   bpe_xchg_attach   map every peer's block
+//   bpe_step_begin / (all-reduce of the byte-pair histogram, once) / bpe_step_table   as above
+//   bpe_step_fused    enqueue n merge iterations: arg-max, tie filter, local first occurrence, candidate
+//                     exchange (ties only), merge, delta exchange fused with the table update
+//   bpe_step_poll / bpe_step_result   as above
+// ================================================================================================
+static void xchg_close_peers(bpe_handle *h) {
+    for (int r = 0; r < h->xargs.world; ++r)
+        if (r != h->xargs.rank && h->xargs.peer[r]) { cudaIpcCloseMemHandle(h->xargs.peer[r]); h->xargs.peer[r] = nullptr; }
+    h->xchg_attached = false;
+}
+
+static void xchg_release(bpe_handle *h) {
+    xchg_close_peers(h);
+    if (h->xchg) cudaFree(h->xchg);
+    h->xchg = nullptr; h->xchg_bytes = 0; h->xchg_V = 0;
+    memset(&h->xargs, 0, sizeof(h->xargs));
+}
+
+extern "C" int bpe_xchg_create(bpe_handle *h, int32_t world, int32_t rank, int32_t vocab_cap, uint8_t *ipc_handle_out) {
+    if (!h || world < 1 || world > XCHG_MAX_RANKS || rank < 0 || rank >= world || vocab_cap < 256 || !ipc_handle_out) return BPE_ERR_ARG;
+    static_assert(sizeof(cudaIpcMemHandle_t) == 64, "IPC handle size");
+    CU(cudaSetDevice(h->device));
+    CU(cudaStreamSynchronize(h->stream));
+    xchg_release(h);
+    const u64 stride = ((2ull * (u64)vocab_cap + 1) * 8 + 255) & ~255ull;
+    const u64 bytes = XCHG_HDR_BYTES + 2 * stride;
+    CU(cudaMalloc(&h->xchg, bytes));
+    CU(cudaMemset(h->xchg, 0, bytes));
+    h->xchg_bytes = bytes; h->xchg_stride = stride; h->xchg_V = (u32)vocab_cap;
+    h->xargs.world = world; h->xargs.rank = rank; h->xargs.delta_stride = stride;
+    h->xargs.peer[rank] = h->xchg;
+    cudaIpcMemHandle_t ipc;
+    CU(cudaIpcGetMemHandle(&ipc, h->xchg));
+    memcpy(ipc_handle_out, &ipc, 64);
+    if (world == 1) h->xchg_attached = true;
+    return BPE_OK;
+}
+
+// Unmap the peers' blocks.  A block must not be freed (bpe_xchg_create again, bpe_destroy) while another process
+// still maps it: every rank detaches, the host synchronises the ranks, then the blocks may go.
+extern "C" int bpe_xchg_detach(bpe_handle *h) {
+    if (!h) return BPE_ERR_ARG;
+    CU(cudaSetDevice(h->device));
+    CU(cudaStreamSynchronize(h->stream));
+    xchg_close_peers(h);
+    return BPE_OK;
+}
+
+extern "C" int bpe_xchg_attach(bpe_handle *h, const uint8_t *all_handles) {
+    if (!h || !all_handles) return BPE_ERR_ARG;
+    if (!h->xchg) return fail(h, BPE_ERR_STATE, "call bpe_xchg_create first");
+    CU(cudaSetDevice(h->device));
+    for (int r = 0; r < h->xargs.world; ++r) {
+        if (r == h->xargs.rank) continue;
+        cudaIpcMemHandle_t ipc;
+        memcpy(&ipc, all_handles + 64 * (size_t)r, 64);
+        void *p = nullptr;
+        cudaError_t e = cudaIpcOpenMemHandle(&p, ipc, cudaIpcMemLazyEnablePeerAccess);
+        if (e != cudaSuccess)
+            return fail(h, BPE_ERR_CUDA, std::string("cudaIpcOpenMemHandle(rank ") + std::to_string(r) + "): " + cudaGetErrorString(e) +
+                                             " (peer access between the GPUs of one NVLink box is required)");
+        h->xargs.peer[r] = (unsigned char *)p;
+    }
+    h->xchg_attached = true;
+    return BPE_OK;
+}
+
+extern "C" int bpe_step_fused(bpe_handle *h, int32_t n_iters) {
+    if (!h || n_iters < 0) return BPE_ERR_ARG;
+    if (!h->xchg_attached) return fail(h, BPE_ERR_STATE, "bpe_step_fused needs bpe_xchg_create + bpe_xchg_attach");
+    if (h->V != h->xchg_V) return fail(h, BPE_ERR_STATE, "exchange block was created for another vocabulary capacity");
+    if (!h->d_present) return fail(h, BPE_ERR_STATE, "call bpe_step_begin / bpe_step_table first");
+    for (int i = 0; i < n_iters; ++i) {
+        k_argmax<<<h->argmax_grid, 256, 0, h->stream>>>(h->table, h->ctl, h->partials, h->log_pairs, h->log_counts);
+        k_tie_present<<<h->argmax_grid, 256, 0, h->stream>>>(h->table, h->ctl, h->d_present);
+        k_find_first<<<h->ff_grid, 256, 0, h->stream>>>(h->buf[0], h->buf[1], h->edge[0], h->edge[1], h->table, h->ctl,
+                                                        h->log_pairs, h->log_counts, 1);
+        k_xchg_cand<<<1, 32, 0, h->stream>>>(h->ctl, h->xargs, h->log_pairs, h->log_counts);
+        timed_merge(h, nullptr, true);
+        k_xchg_apply<<<(h->V + 255) / 256, 256, 0, h->stream>>>(h->table, h->ctl, h->xargs, h->V, h->d_present);
+        h->tm.kernel_launches += 5;
+    }
+    CU(cudaGetLastError());
     return BPE_OK;
 }

@@ -12,7 +12,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.environ.get("BPE_LIB_PATH") or os.path.join(_HERE, "csrc", "libb200bpe.so")  # override: A/B builds
 ABI_VERSION = 1
 
-OPT_KERNEL_TIMING, OPT_RESCAN, OPT_BATCH, OPT_TABLE_LOG2 = 1, 2, 3, 4
+OPT_KERNEL_TIMING, OPT_RESCAN, OPT_BATCH, OPT_TABLE_LOG2, OPT_SPLIT_PIECE, OPT_VOCAB_CAP, OPT_ENC_MEMO_LOG2 = 1, 2, 3, 4, 5, 6, 7
 ERR_CAPACITY = -4
 
 _lib = None
@@ -56,6 +56,8 @@ def load_library():
         "bpe_merge": ([vp, i32, i32, i32, P(u64)], ci),
         "bpe_train": ([vp, i32, i32, vp, vp, P(i32)], ci),
         "bpe_encode": ([vp, vp, u64, vp, u64, vp, i32, vp, vp, u64, P(u64)], ci),
+        "bpe_encode_text_gpt4": ([vp, vp, u64, vp, i32, vp, vp, u64, P(u64)], ci),
+        "bpe_encode_stats": ([vp, vp], ci),
         "bpe_get_timing": ([vp, P(Timing)], ci),
         "bpe_set_option": ([vp, ci, i64], ci),
         "bpe_debug_table": ([vp, vp, vp, u64, P(u64)], ci),
@@ -72,6 +74,10 @@ def load_library():
         "bpe_step_delta_len": ([vp, P(u64)], ci),
         "bpe_step_poll": ([vp, P(i32), P(i32)], ci),
         "bpe_step_result": ([vp, vp, vp, i32, P(i32)], ci),
+        "bpe_xchg_create": ([vp, i32, i32, i32, vp], ci),
+        "bpe_xchg_attach": ([vp, vp], ci),
+        "bpe_xchg_detach": ([vp], ci),
+        "bpe_step_fused": ([vp, i32], ci),
     }
     for name, (args, res) in sig.items():
         fn = getattr(L, name)  # AttributeError here = header/library mismatch
@@ -206,6 +212,25 @@ class Engine:
             return out[: n.value].tobytes(), -1
         raise EngineError("bpe_decode: capacity retry failed")
 
+    def encode_text_gpt4(self, data, merges, byte_perm=None, out=None):
+        """-> ids int32 of utf-8 `data`: GPT-4 split + encode, both on the GPU (regex.py:111-121)."""
+        self._ensure_gpt4_tables()
+        b = np.frombuffer(data, dtype=np.uint8) if not isinstance(data, np.ndarray) else np.ascontiguousarray(data, dtype=np.uint8)
+        m = np.ascontiguousarray(np.asarray(merges, dtype=np.int32).reshape(-1, 2))
+        perm = None if byte_perm is None else np.ascontiguousarray(byte_perm, dtype=np.uint8)
+        if out is None:
+            out = np.empty(max(b.size, 1), dtype=np.int32)
+        n = ctypes.c_uint64()
+        self._check(self._lib.bpe_encode_text_gpt4(self._h, _ptr(b) if b.size else None, b.size, _ptr(m) if m.size else None,
+                                                   m.shape[0], _ptr(perm), _ptr(out), out.size, ctypes.byref(n)), "bpe_encode_text_gpt4")
+        return out[: n.value]
+
+    def encode_stats(self):
+        a = np.zeros(8, dtype=np.uint64)
+        self._check(self._lib.bpe_encode_stats(self._h, _ptr(a)), "bpe_encode_stats")
+        names = ("memo_chunks", "pool_ids", "new_chunks", "direct_chunks", "long_chunks", "pieces", "fallback_pieces", "kernel_us")
+        return {k: int(v) for k, v in zip(names, a)}
+
     # ---- measurement / options ----
     def timing(self):
         t = Timing()
@@ -280,6 +305,22 @@ class Engine:
 
     def step_apply(self, delta_ptr):
         self._check(self._lib.bpe_step_apply(self._h, ctypes.c_void_p(delta_ptr)), "bpe_step_apply")
+
+    def xchg_create(self, world, rank, vocab_cap):
+        """Allocate this rank's NVLink exchange block; -> its 64-byte CUDA IPC handle (uint8 array)."""
+        out = np.zeros(64, dtype=np.uint8)
+        self._check(self._lib.bpe_xchg_create(self._h, int(world), int(rank), int(vocab_cap), _ptr(out)), "bpe_xchg_create")
+        return out
+
+    def xchg_attach(self, all_handles):
+        a = np.ascontiguousarray(all_handles, dtype=np.uint8).reshape(-1)
+        self._check(self._lib.bpe_xchg_attach(self._h, _ptr(a)), "bpe_xchg_attach")
+
+    def xchg_detach(self):
+        self._check(self._lib.bpe_xchg_detach(self._h), "bpe_xchg_detach")
+
+    def step_fused(self, n_iters):
+        self._check(self._lib.bpe_step_fused(self._h, int(n_iters)), "bpe_step_fused")
 
     def step_poll(self):
         it, ex = ctypes.c_int32(), ctypes.c_int32()

@@ -112,6 +112,16 @@ class Tokenizer:
         return self._engine
 
     def _merge_array(self):
+        # cached: built once per merges dict (a 32k-entry table costs ~10 ms of Python per encode call otherwise)
+        n = len(self.merges)
+        stamp = (id(self.merges), n, next(reversed(self.merges.items())) if n else None)
+        if getattr(self, "_merge_cache", (None, None))[0] == stamp:
+            return self._merge_cache[1]
+        m = self._merge_array_build()
+        self._merge_cache = (stamp, m)
+        return m
+
+    def _merge_array_build(self):
         m = np.empty((len(self.merges), 2), dtype=np.int32)
         for r, (pair, idx) in enumerate(self.merges.items()):
             if idx != 256 + r:
@@ -130,6 +140,10 @@ class Tokenizer:
             eng.load_stream(data, offsets)
         pairs, counts, done = eng.train(num_merges)
         self.last_timing = eng.timing()
+        self._adopt(pairs, counts, done, num_merges, verbose)
+
+    def _adopt(self, pairs, counts, done, num_merges, verbose):
+        """basic.py:37-45: merges / vocab (and the verbose lines) from the pairs the device loop chose."""
         merges = {}
         vocab = {i: bytes((i,)) for i in range(256)}
         for i in range(done):
@@ -299,6 +313,21 @@ class RegexTokenizer(Tokenizer):
         data, offsets = split_text(self.compiled_pattern, text)
         self._run_training(data, offsets, vocab_size, verbose)
 
+    def train_from_file(self, path, vocab_size, verbose=False, *, group=None):
+        """train() for a UTF-8 text file of any size (not in the reference, which takes a str: regex.py:36).  The file
+        is memory-mapped and split on the device in pieces; when torch.distributed is initialised (one process per
+        GPU) every rank trains on its own byte range — cut where a letter is followed by a space, a provable chunk
+        boundary — and all ranks end with identical merges / vocab.  GPT-4 split pattern only."""
+        assert vocab_size >= 256
+        if self.compiled_pattern.pattern != GPT4_SPLIT_PATTERN:
+            raise ValueError("train_from_file splits on the device and supports the GPT-4 split pattern only; "
+                             "use train(open(path).read(), ...) for other patterns")
+        from .dist import train_file
+        eng = self.engine
+        pairs, counts, done = train_file(eng, eng.device, path, vocab_size - 256, group=group)
+        self.last_timing = eng.timing()
+        self._adopt(pairs, counts, done, vocab_size - 256, verbose)
+
     def register_special_tokens(self, special_tokens):
         self.special_tokens = special_tokens
         self.inverse_special_tokens = {idx: text for text, idx in special_tokens.items()}
@@ -331,7 +360,7 @@ class RegexTokenizer(Tokenizer):
         """regex.py:111-121."""
         raw = text.encode("utf-8")
         if self.merges and self._device_split(len(raw)):
-            return self.engine.encode(raw, self.engine.split_gpt4(raw), self._merge_array()).tolist()
+            return self.engine.encode_text_gpt4(raw, self._merge_array()).tolist()   # split + encode on the device, no offsets
         data, offsets = split_text(self.compiled_pattern, text)
         if not self.merges or len(data) < 2:
             return list(data)

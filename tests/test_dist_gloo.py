@@ -92,3 +92,55 @@ def test_shard_chunks_cover_and_respect_chunks():
                 assert a1 == b0 and c1 == d0
             for lo, hi, c0, c1 in spans:
                 assert lo <= hi and (lo == n or lo in offs)
+
+
+def test_shard_byte_range_cuts_are_chunk_boundaries(taylorswift):
+    """Byte-range shards (files, generated corpora): every interior cut must be a boundary of the regex split of the
+    WHOLE text, for any world size — then the ranks' chunk lists concatenate to RegexTokenizer's (regex.py:41)."""
+    import regex
+    from minbpe_b200.dist import first_safe_cut, shard_byte_range
+    from minbpe_b200.synth import generate
+    from minbpe_b200.tokenizer import GPT2_SPLIT_PATTERN, GPT4_SPLIT_PATTERN
+    texts = [taylorswift, generate(1337, 3 << 20).tobytes().decode("utf-8"),
+             "word " * 10 + "   \n  spaces   and ends " * 2000 + "tail"]
+    for pat in (GPT4_SPLIT_PATTERN, GPT2_SPLIT_PATTERN):
+        cp = regex.compile(pat)
+        for text in texts:
+            raw = np.frombuffer(text.encode("utf-8"), dtype=np.uint8)
+            whole = cp.findall(text)
+            for world in (1, 2, 3, 8):
+                parts, prev_hi = [], 0
+                for r in range(world):
+                    lo, hi = shard_byte_range(raw.size, r, world, lambda a, b: raw[a:b], window=1 << 16)
+                    assert lo == prev_hi and lo <= hi
+                    prev_hi = hi
+                    parts += cp.findall(raw[lo:hi].tobytes().decode("utf-8"))
+                assert prev_hi == raw.size
+                assert parts == whole, (pat[:12], world)
+    assert first_safe_cut(np.frombuffer(b"12 34 a b", dtype=np.uint8)) == 7
+    assert first_safe_cut(np.frombuffer(b"  \n12", dtype=np.uint8)) == -1
+    with pytest.raises(ValueError):
+        shard_byte_range(100, 1, 2, lambda a, b: np.frombuffer(b"1" * (b - a), dtype=np.uint8))
+
+
+def test_bench_unique_chunk_merge_equals_plain_oracle():
+    """bench.py's cfg4 parity check merges per-piece / per-rank tables of distinct chunks: the weighted oracle loop
+    over the merged table must equal the plain loop over the whole text (regex.py:51-54: one dict across chunks)."""
+    import regex
+    import bench
+    from minbpe_b200.synth import generate
+    from minbpe_b200.tokenizer import GPT4_SPLIT_PATTERN
+    text = generate(1337, 1 << 20).tobytes().decode("utf-8")
+    data, offs = oracle.split_to_stream(text, regex.compile(GPT4_SPLIT_PATTERN))
+    want = oracle.c_train(data.astype(np.int32), offs, 80)
+    k = len(offs)
+    parts = []
+    for a, b in ((0, k // 3), (k // 3, k // 2), (k // 2, k)):
+        lo, hi = int(offs[a]), (int(offs[b]) if b < k else data.size)
+        ub, uo, uw = oracle.c_dedup_chunks(data[lo:hi], offs[a:b] - offs[a])
+        ends = np.append(uo[1:], ub.size).astype(np.int64)
+        blob = ub.tobytes()
+        parts.append(([blob[int(x):int(y)] for x, y in zip(uo.astype(np.int64), ends)], uw))
+    chunks, weights = bench.merge_unique(parts)
+    got = bench.oracle_train_unique(chunks, weights, 80)
+    assert got[2] == want[2] == 80 and np.array_equal(got[0], want[0]) and np.array_equal(got[1], want[1])

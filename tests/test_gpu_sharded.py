@@ -24,14 +24,17 @@ def corpus():
     return oracle.split_to_stream(text, GPT4)
 
 
-def test_step_api_world1():
+@pytest.mark.parametrize("exchange", ["p2p", "collective"])
+def test_step_api_world1(exchange):
+    """p2p = the NVLink exchange kernels (k_xchg_cand / k_xchg_apply) with this rank as its only peer;
+    collective = the host-sequenced step API (no collective needed at world 1)."""
     import torch
     from minbpe_b200.dist import GpuStepEngine, ShardedTrainer
     from minbpe_b200.engine import Engine
     data, offs = corpus()
     eng = Engine(0)
     eng.load_stream(data, offs)
-    tr = ShardedTrainer(GpuStepEngine(eng, 0), rank=0, world=1, poll_every=7)
+    tr = ShardedTrainer(GpuStepEngine(eng, 0), rank=0, world=1, poll_every=7, exchange=exchange)
     tr.prepare(60)
     done, exhausted = tr.run()
     pairs, counts, n = tr.result()
@@ -42,7 +45,7 @@ def test_step_api_world1():
     eng.close()
 
 
-def _rank_main(rank, world, port, q):
+def _rank_main(rank, world, port, q, exchange="p2p"):
     sys.path.insert(0, ROOT)
     os.environ["MASTER_ADDR"] = "127.0.0.1"
     os.environ["MASTER_PORT"] = str(port)
@@ -55,21 +58,25 @@ def _rank_main(rank, world, port, q):
         from minbpe_b200.engine import Engine
         data, offs = corpus()
         eng = Engine(rank)
-        pairs, counts, n = train_sharded(eng, rank, data, offs, 60, poll_every=7)
+        pairs, counts, n = train_sharded(eng, rank, data, offs, 60, poll_every=7, exchange=exchange)
+        # a second run on the same engine: the exchange block is reused (sequence numbers keep growing)
+        p2, c2, n2 = train_sharded(eng, rank, data, offs, 30, poll_every=16, exchange=exchange)
+        assert n2 == 30 and np.array_equal(p2, pairs[:30]) and np.array_equal(c2, counts[:30])
         q.put((rank, pairs.tolist(), counts.tolist(), n))
         eng.close()
     finally:
         dist.destroy_process_group()
 
 
-def test_step_api_world2_nccl():
+@pytest.mark.parametrize("exchange", ["p2p", "collective"])
+def test_step_api_world2_nccl(exchange):
     import torch
     if torch.cuda.device_count() < 2:
         pytest.skip("needs 2 GPUs")
     import torch.multiprocessing as mp
     ctx = mp.get_context("spawn")
     q = ctx.Queue()
-    procs = [ctx.Process(target=_rank_main, args=(r, 2, 29621, q)) for r in range(2)]
+    procs = [ctx.Process(target=_rank_main, args=(r, 2, 29621 + (exchange == "p2p"), q, exchange)) for r in range(2)]
     for p in procs:
         p.start()
     out = sorted(q.get(timeout=300) for _ in procs)

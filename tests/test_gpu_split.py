@@ -68,3 +68,34 @@ def test_load_text_equals_load_stream(eng, taylorswift):
     assert n_chunks == len(offs)
     p2, c2, d2 = eng.train(100)
     assert d1 == d2 == 100 and np.array_equal(p1, p2) and np.array_equal(c1, c2)
+
+
+def test_piecewise_split_equals_whole(eng, taylorswift):
+    """Texts beyond one split call (1 GiB pieces by default) are cut where an ASCII letter is followed by U+0020
+    (a provable chunk boundary of the GPT-4 pattern).  With the piece size forced down to 64 KiB the
+    same code path runs on small texts: offsets, chunk counts and the marked training stream must not change."""
+    from minbpe_b200 import engine as E
+    from minbpe_b200.synth import generate
+    texts = [taylorswift, generate(1337, 8 << 20).tobytes().decode("utf-8")]
+    try:
+        for text in texts:
+            data, offs = want_offsets(text)
+            raw = data.tobytes()
+            for piece in (1 << 16, (1 << 20) + 4096):
+                eng.set_option(E.OPT_SPLIT_PIECE, piece)
+                assert np.array_equal(eng.split_gpt4(raw), offs)
+                assert eng.load_text_gpt4(raw, count_chunks=True) == len(offs)
+                p1, c1, d1 = eng.train(24)
+                eng.load_text_gpt4(raw)          # the marks-straight-from-the-rule-kernel path
+                p2, c2, d2 = eng.train(24)
+                eng.set_option(E.OPT_SPLIT_PIECE, 0)
+                eng.load_stream(data, offs)
+                p0, c0, d0 = eng.train(24)
+                assert d0 == d1 == d2 == 24
+                assert np.array_equal(p0, p1) and np.array_equal(c0, c1) and np.array_equal(p0, p2) and np.array_equal(c0, c2)
+        # a text without any letter+space inside a piece cannot be cut: a clean error, not a wrong split
+        eng.set_option(E.OPT_SPLIT_PIECE, 4096)
+        with pytest.raises(E.EngineError):
+            eng.split_gpt4(("12345 " * 4000).encode())
+    finally:
+        eng.set_option(E.OPT_SPLIT_PIECE, 0)
