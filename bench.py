@@ -86,6 +86,49 @@ def pin_host(arr):
         return False
 
 
+def unpin_host(arr):
+    import torch
+    try:
+        torch.cuda.cudart().cudaHostUnregister(arr.ctypes.data)
+    except Exception:  # noqa: BLE001
+        pass
+
+
+class Watchdog:
+    """The contract is ONE JSON line.  The later legs of a run (whole-loop run, cfg4, cfg5) are optional detail: if one
+    of them hangs, this timer prints the line with what has been measured so far and ends the process, instead of
+    leaving the driver without a number."""
+
+    def __init__(self, seconds):
+        self.line, self.timer, self.seconds = None, None, seconds
+
+    def arm(self, line):
+        self.line = line
+        if self.timer is None and self.seconds > 0:
+            self.timer = threading.Timer(self.seconds, self._fire)
+            self.timer.daemon = True
+            self.timer.start()
+
+    def _fire(self):
+        if self.line is not None:
+            self.line["watchdog"] = f"a later leg did not finish within {self.seconds} s; line printed by the watchdog"
+            print(json.dumps(self.line), flush=True)
+        os._exit(0)
+
+    def disarm(self):
+        if self.timer is not None:
+            self.timer.cancel()
+
+
+def guarded(name, fn, *a):
+    """Run an optional leg; a failure becomes {"error": ...} in the line instead of losing the whole run."""
+    try:
+        return fn(*a)
+    except Exception as ex:  # noqa: BLE001
+        import traceback
+        return {"error": f"{name}: {ex!r}", "traceback": traceback.format_exc()[-1500:]}
+
+
 class ClockSampler:
     """nvidia-smi clocks / throttle reasons sampled DURING the timed region."""
     Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
@@ -432,6 +475,7 @@ def strong_leg(args, eng, rank, world, local):
     load_s = tmax(time.perf_counter() - t0)
     eng.set_option(E.OPT_KERNEL_TIMING, 0)
     windows = {}
+    exchange_used, exchange_fallback = None, None
     if world == 1:
         eng.set_option(E.OPT_VOCAB_CAP, vocab)
         done_total, all_pairs = 0, []
@@ -476,6 +520,7 @@ def strong_leg(args, eng, rank, world, local):
         window(K, "sparse")
         pairs, _, n = tr.result()
         pairs = pairs[:n]
+        exchange_used, exchange_fallback = tr.exchange, getattr(tr, "exchange_fallback", None)
     # ---- parity: first P merges vs the oracle over the distinct chunks of the whole corpus ----
     P = min(args.strong_check, len(pairs))
     parity = None
@@ -494,16 +539,133 @@ def strong_leg(args, eng, rank, world, local):
                       "how": "oracle.c_train(weights) over the distinct chunks of the whole corpus (device split of every rank's "
                              "shard, host de-duplication, tables merged in rank = text order)"}
     if world > 1:
-        step.e.xchg_detach()
+        try:
+            step.e.xchg_detach()
+        except Exception:  # noqa: BLE001
+            pass
         sync()
     out = {"workload": f"BASELINE configs[3]: RegexTokenizer.train, {args.strong_gib} GiB synthetic UTF-8 (seed 1338), vocab {vocab}, "
                        f"{world} GPU(s), contiguous byte-range shards cut at letter+space", "scaling": "strong",
            "bytes_total": total, "bytes_this_rank": int(hi - lo), "vocab": vocab, "delta_vector_bytes": (2 * vocab + 1) * 8,
-           "exchange": "none (1 GPU)" if world == 1 else "NVLink peer memory kernels (k_xchg_cand on ties + k_xchg_apply), no NCCL per merge",
+           "exchange": "none (1 GPU)" if world == 1 else (
+               "NVLink peer memory kernels (k_xchg_cand on ties + k_xchg_apply), no NCCL per merge" if exchange_used == "p2p" else
+               "torch.distributed all-reduce MIN + SUM per merge (fallback: " + str(exchange_fallback) + ")"),
            "nvlink_pull_bytes_per_merge_per_rank": 0 if world == 1 else (world - 1) * (2 * vocab + 1) * 8,
            "generate_s": round(gen_s, 1), "load_seconds": load_s, "windows": windows,
            "merges_sha16": merges_sha(pairs), "merges_in_sha": int(len(pairs)), "parity_vs_oracle": parity}
     return out
+
+
+def encode_leg(args, eng, rank, world, merges):
+    """BASELINE configs[4] (cfg5): RegexTokenizer.encode_ordinary of `encode_gb` * 1e9 bytes of synthetic UTF-8 (seed 1339)
+    with a trained 32k merges table, through the C ABI call a user makes (bpe_encode_text_gpt4: host text in, host ids
+    out; H2D, GPT-4 split, memoised chunk encode and D2H all inside the timed region).  N GPUs = N replicas over byte-range
+    shards (chunks are independent: no exchange).  Reports the end-to-end rate, the device time of the encode kernels
+    against the HBM roofline (algorithmic bytes: 1 B per text byte + 4 B per id), the split kernels'
+    time beside it, the oracle port (and the pure-Python reference) on a slice, and bit-exactness of a slice."""
+    import torch
+    import torch.distributed as dist
+    import oracle
+    from minbpe_b200 import engine as E
+    from minbpe_b200.dist import first_safe_cut
+    total = int(args.encode_gb * 1e9) // (1 << 20) * (1 << 20)
+    threads = max(1, host_cores() // world)
+    raw, lo, hi = corpus_shard(1339, total, rank, world, threads)
+    raw = np.ascontiguousarray(raw)
+    pinned = pin_host(raw)
+    out = np.empty(raw.size // 2 + 1024, dtype=np.int32)     # ids: at most one per byte, ~0.3 per byte in practice
+    pin_host(out)
+    eng.set_option(E.OPT_KERNEL_TIMING, 0)
+    wcut = min(raw.size, 64 << 20)
+    if wcut < raw.size:
+        wcut += max(0, first_safe_cut(raw[wcut: wcut + (1 << 20)]))
+    ids = eng.encode_text_gpt4(raw[:wcut], merges, out=out)    # warm-up: tables, allocations (the memo stays warm, as for a user)
+    runs = []
+    for _ in range(3):
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        t0 = time.perf_counter()
+        ids = eng.encode_text_gpt4(raw, merges, out=out)
+        runs.append(time.perf_counter() - t0)
+    tm = eng.timing()
+    t = sorted(runs)[1]
+    # device time of the kernels, separately (events inside the library, one more run)
+    eng.set_option(E.OPT_KERNEL_TIMING, 1)
+    ids = eng.encode_text_gpt4(raw, merges, out=out)
+    st = eng.encode_stats()
+    split_ms = eng.timing()["init_ms"]
+    eng.set_option(E.OPT_KERNEL_TIMING, 0)
+    enc_s = st["kernel_us"] / 1e6
+    tt = torch.tensor([t, enc_s, split_ms / 1e3, float(raw.size), float(ids.size)], device="cuda", dtype=torch.float64)
+    if world > 1:
+        mx = tt.clone(); dist.all_reduce(mx, op=dist.ReduceOp.MAX)
+        sm = tt.clone(); dist.all_reduce(sm, op=dist.ReduceOp.SUM)
+        t, enc_s, split_s, nbytes, nids = float(mx[0]), float(mx[1]), float(mx[2]), float(sm[3]), float(sm[4])
+    else:
+        t, enc_s, split_s, nbytes, nids = t, enc_s, split_ms / 1e3, float(raw.size), float(ids.size)
+    res = None
+    if rank == 0:
+        peak, _ = measured_peak()
+        # parity + CPU baseline on a slice of rank 0's shard, cut where chunking cannot differ
+        # (single-process regex: this process holds pinned host buffers and a CUDA context — no fork() from here)
+        cut = (16 << 20) + max(0, first_safe_cut(raw[16 << 20: (16 << 20) + (1 << 20)]))
+        from minbpe_b200.presplit import chunk_offsets_1proc
+        import regex
+        o2 = chunk_offsets_1proc(regex.compile(GPT4), raw[:cut].tobytes())
+        t0 = time.perf_counter()
+        want = oracle.c_encode(raw[:cut], o2, merges)
+        dt = time.perf_counter() - t0
+        same = bool(np.array_equal(ids[: want.size], want))
+        py = None
+        try:
+            from oracle import make_ref
+            ref = make_ref.load()
+            if ref is not None:
+                tokr = ref.RegexTokenizer()
+                tokr.merges = {(int(a), int(b)): 256 + i for i, (a, b) in enumerate(np.asarray(merges).tolist())}
+                tokr.vocab = tokr._build_vocab()
+                c2 = (1 << 20) + max(0, first_safe_cut(raw[1 << 20: (1 << 20) + (1 << 16)]))
+                txt = raw[:c2].tobytes().decode("utf-8")
+                t0 = time.perf_counter(); rid = tokr.encode_ordinary(txt); pdt = time.perf_counter() - t0
+                py = {"value": c2 / pdt / 1e9, "unit": "GB/s", "cores": 1, "kind": "reference", "seconds": pdt,
+                      "equal_ids": bool(rid == ids[: len(rid)].tolist()),
+                      "sample": f"karpathy/minbpe RegexTokenizer.encode_ordinary (pure Python) on the first {c2} bytes"}
+        except Exception as ex:  # noqa: BLE001
+            py = {"error": repr(ex)}
+        alg = nbytes + 4.0 * nids
+        res = {"workload": f"BASELINE configs[4]: RegexTokenizer.encode_ordinary, {total} bytes synthetic UTF-8 (seed 1339), "
+                           f"{len(merges)} merges, {world} GPU(s) (replicas over byte-range shards)",
+               "metric": "encode_text_GBps", "value": nbytes / t / 1e9, "unit": "GB/s", "seconds": t, "runs_seconds": runs,
+               "bytes": nbytes, "ids": nids, "ids_per_s": nids / t,
+               "e2e": {"value": nbytes / t / 1e9, "unit": "GB/s", "h2d_bytes": float(tm["h2d_bytes"]), "d2h_bytes": float(tm["d2h_bytes"]),
+                       "host_buffer": "pinned (cudaHostRegister)" if pinned else "pageable",
+                       "what": "bpe_encode_text_gpt4(host text -> host ids): H2D + GPT-4 split + encode + D2H, wall clock, median of 3, max over ranks"},
+               "kernels": {"encode_s": enc_s, "split_s": split_s, "encode_text_GBps": nbytes / world / enc_s / 1e9 * world,
+                           "what": "device time (CUDA events in the library) of k_enc_insert/distinct/direct/count/scan/write, and of the 4 split kernels; max over ranks"},
+               "roofline": {"bound": "hbm", "kernel": "k_enc_* (memoised chunk encode: insert + count + write passes)", "unit": "GB/s",
+                            "achieved": alg / world / enc_s / 1e9, "peak": peak, "frac": alg / world / enc_s / 1e9 / peak,
+                            "algorithmic_bytes": alg, "per_unit": "1 B read per text byte + 4 B written per id"},
+               "memo": {k: st[k] for k in ("memo_chunks", "pool_ids", "direct_chunks", "long_chunks", "pieces", "fallback_pieces")},
+               "cpu_baseline": {"value": cut / dt / 1e9, "unit": "GB/s", "cores": 1, "kind": "port", "seconds": dt,
+                                "sample": f"oracle/bpe_oracle.c orc_encode (regex.py:92-121 restated in C) on the first {cut} bytes, single thread",
+                                "python_reference": py},
+               "parity": {"equal": same, "ids_checked": int(want.size), "how": "ids of the first slice == oracle.c_encode(host regex split of that slice)"}}
+    if pinned:
+        try:
+            torch.cuda.cudart().cudaHostUnregister(raw.ctypes.data)
+            torch.cuda.cudart().cudaHostUnregister(out.ctypes.data)
+        except Exception:  # noqa: BLE001
+            pass
+    return res
+
+
+def merges_for_encode(eng, n_merges):
+    """A trained table for the encode leg when the run has none yet: RegexTokenizer.train on 256 MiB of the cfg3 corpus."""
+    from minbpe_b200.synth import generate
+    eng.load_text_gpt4(generate(1337, 256 << 20))
+    p, _, d = eng.train(n_merges)
+    return p[:d]
 
 
 def run_sharded(args, rank, world, local):
@@ -580,7 +742,7 @@ def run_sharded(args, rank, world, local):
     merge_ms = torch.tensor([tm["merge_kernel_ms"] / max(n, 1)], device="cuda")   # CUDA events around the merge launches, all W+K steps
     merge_all = [torch.zeros_like(merge_ms) for _ in range(world)]
     dist.all_gather(merge_all, merge_ms)
-    strong = strong_leg(args, eng, rank, world, local) if args.strong_gib > 0 else None
+    line = None
     if rank == 0:
         t = float(t_loop.item())
         peak, peak_src = measured_peak()
@@ -596,6 +758,7 @@ def run_sharded(args, rank, world, local):
                                    f"letter+space (a provable chunk boundary), merge steps {W}..{W + K - 1}; per merge: candidate push on "
                                    f"ties + delta pull/sum fused with the table update, over NVLink peer memory (k_xchg.cuh), no NCCL call",
                        "parallelism": f"shard{world}", "prep_s": round(prep_s, 1), "consistent": bool(ok),
+                       "exchange_used": tr.exchange, "exchange_fallback_reason": getattr(tr, "exchange_fallback", None),
                        "shard_bytes_rank0": int(hi - lo),
                        "l2": "per-GPU stream >> 126 MB L2, re-read from HBM every step",
                        "timing": "CUDA events on the shared stream, max over ranks, barrier + synchronize on both sides"},
@@ -606,25 +769,41 @@ def run_sharded(args, rank, world, local):
                           "select_exchange_apply": k_ms - max(float(x.item()) for x in merge_all),
                           "how": "merge = CUDA events around the merge launches (every rank); the rest of the step = arg-max, tie filter, "
                                  "first-occurrence scan, candidate exchange, delta exchange + table update, and waiting for the slowest rank"},
-            "exchange": {"kind": "NVLink peer memory (CUDA IPC), hand-written kernels", "delta_vector_bytes": (2 * V + 1) * 8,
+            "exchange": {"kind": "NVLink peer memory (CUDA IPC), hand-written kernels" if tr.exchange == "p2p" else
+                                 "torch.distributed all-reduce MIN + SUM per merge (fallback: " + str(getattr(tr, "exchange_fallback", None)) + ")",
+                         "delta_vector_bytes": (2 * V + 1) * 8,
                          "nvlink_pull_bytes_per_merge_per_rank": (world - 1) * (2 * V + 1) * 8,
                          "candidate_push_bytes_per_tie_per_rank": (world - 1) * 16},
             "roofline": {"bound": "hbm", "kernel": "k_merge_seg (rank 0; rate over the whole step incl. exchanges)",
                          "achieved": bytes_per_launch / (k_ms / 1e3) / 1e9, "peak": peak, "unit": "GB/s",
                          "frac": bytes_per_launch / (k_ms / 1e3) / 1e9 / peak, "traffic": None, "peak_source": peak_src, "ms_per_launch": k_ms},
             "cpu_baseline": None,
-            "strong_cfg4": strong,
+            "strong_cfg4": None, "encode_cfg5": None,
             "e2e": {"value": size * world * (W + K) / float(t_e2e.item()) / 1e9, "unit": "GB/s",
                     "h2d_bytes_per_step": h2d / (W + K), "d2h_bytes_per_step": 16.0, "seconds": float(t_e2e.item()),
                     "host_buffer": "pinned (cudaHostRegister)" if pinned else "pageable",
                     "what": "per rank: bpe_load_text_gpt4(host shard text: H2D + device split) + sharded loop of W+K merges + merges D2H, wall clock, max over ranks"},
             "first_pairs": pairs[W:W + 4].tolist(), "merges_sha16": merges_sha(pairs[: W + K]),
         }
+    # ---- optional detail legs (every rank arms the same watchdog: a leg that hangs ends all ranks, rank 0 printing the
+    #      contract line as it stands; a leg that raises on every rank is reported as {"error": ...}) ----
+    dog = Watchdog(args.leg_budget_s)
+    dog.arm(line)
+    if pinned:
+        unpin_host(raw)
+    strong = guarded("strong_cfg4", strong_leg, args, eng, rank, world, local) if args.strong_gib > 0 else None
+    enc = guarded("encode_cfg5", lambda: encode_leg(args, eng, rank, world, merges_for_encode(eng, 32512))) if args.encode_gb > 0 else None
+    dog.disarm()
+    if rank == 0:
+        line["strong_cfg4"], line["encode_cfg5"] = strong, enc
         print(json.dumps(line), flush=True)
-    step.e.xchg_detach()
-    sync_all()
-    eng.close()
-    dist.destroy_process_group()
+    try:
+        step.e.xchg_detach()
+        sync_all()
+        eng.close()
+        dist.destroy_process_group()
+    except Exception:  # noqa: BLE001
+        pass
 
 
 # ---------------------------------------------------------------------------------------------
@@ -703,12 +882,6 @@ def run_ours(args):
     peak, peak_src = measured_peak()
     k_ms = tm["merge_kernel_ms"] / K
     achieved = (4.0 * n_in + 4.0 * n_out) / K / (k_ms / 1e3) / 1e9
-    full = None
-    if args.full_merges > 0:
-        full, _ = full_run(eng, raw, offs, args.full_merges, check=not args.no_cpu_baseline)
-    strong = None
-    if args.strong_gib > 0:
-        strong = strong_leg(args, eng, 0, 1, local)
     line = {
         "metric": "train_loop_corpus_GBps", "value": value, "unit": "GB/s", "n_gpus": 1, "steps": K, "warmup": W,
         "ms_per_step": t_loop / K * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
@@ -730,16 +903,36 @@ def run_ours(args):
                      "peak_source": peak_src, "bytes_per_launch": (4.0 * n_in + 4.0 * n_out) / K, "ms_per_launch": k_ms,
                      "loop_frac_in_kernel": tm["merge_kernel_ms"] / tm["loop_ms"]},
         "cpu_baseline": cpu,
-        "full_run": full,
-        "strong_cfg4": strong,
+        "full_run": None, "strong_cfg4": None, "encode_cfg5": None,
         "e2e": {"value": size * (W + K) / t_e2e / 1e9, "unit": "GB/s", "h2d_bytes_per_step": h2d / (W + K),
                 "d2h_bytes_per_step": d2h / (W + K), "seconds": t_e2e, "merges": W + K,
                 "load_seconds": t_load, "runs_seconds": [r[0] for r in e2e_runs], "host_buffer": "pinned (cudaHostRegister)" if pinned else "pageable",
                 "what": "bpe_load_text_gpt4(host text: H2D + GPT-4 split on the device) + bpe_train(W+K) + merges D2H, wall clock, median of 3 runs"},
         "first_pairs": pairs[:4].tolist(),
     }
-    eng.close()
+    # ---- optional detail legs.  The contract line above is complete; from here on a leg that fails is reported as
+    #      {"error": ...} and a leg that hangs is cut off by the watchdog, which prints the line as it stands. ----
+    dog = Watchdog(args.leg_budget_s)
+    dog.arm(line)
+    if pinned:
+        unpin_host(raw)      # nothing below reads `raw` by DMA again; later legs pin their own buffers
+    full_pairs = None
+    if args.full_merges > 0:
+        r = guarded("full_run", full_run, eng, raw, offs, args.full_merges, not args.no_cpu_baseline)
+        if isinstance(r, tuple):
+            line["full_run"], full_pairs = r
+        else:
+            line["full_run"] = r
+    if args.strong_gib > 0:
+        line["strong_cfg4"] = guarded("strong_cfg4", strong_leg, args, eng, 0, 1, local)
+    if args.encode_gb > 0:
+        def enc():
+            m = full_pairs if full_pairs is not None else merges_for_encode(eng, 32512)
+            return encode_leg(args, eng, 0, 1, m)
+        line["encode_cfg5"] = guarded("encode_cfg5", enc)
+    dog.disarm()
     print(json.dumps(line), flush=True)
+    eng.close()
 
 
 def run_extras(args):
@@ -821,6 +1014,12 @@ def main():
     ap.add_argument("--strong-vocab", type=int, default=100000)
     ap.add_argument("--strong-sparse-at", type=int, default=1000, help="first merge of the second (sparse) timed window of the strong leg")
     ap.add_argument("--strong-check", type=int, default=256, help="merges of the strong leg compared with the oracle (0 = none)")
+    ap.add_argument("--encode-gb", type=float, default=4.0,
+                    help="also run BASELINE configs[4] (encode this many 1e9 bytes with a 32k merges table; N GPUs = replicas over "
+                         "byte-range shards) and report it as encode_cfg5; 0 = skip")
+    ap.add_argument("--leg-budget-s", type=int, default=900,
+                    help="wall-clock budget of the optional legs (whole-loop run, cfg4, cfg5) after the contract line is complete; "
+                         "when it runs out the line is printed with the legs finished so far")
     ap.add_argument("--extras", action="store_true", help="side measurements (cfg2 wall time, encode throughput)")
     args = ap.parse_args()
     if args.warmup < 3 and args.impl == "ours":

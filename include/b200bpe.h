@@ -101,6 +101,13 @@ int bpe_merge(bpe_handle *h, int32_t a, int32_t b, int32_t idx, uint64_t *new_le
 int bpe_train(bpe_handle *h, int32_t num_merges, int32_t first_idx,
               int32_t *out_pairs, int64_t *out_counts, int32_t *n_done);
 
+/* Resume (base.py:140-165 load(), then more training): bring the freshly loaded BYTE stream (bpe_load_stream /
+ * bpe_load_text_gpt4) to the state a training run has after the given merges — they are applied in rank order with
+ * the training kernels, the pair table is maintained on the way — so that
+ *     bpe_train(h, more, 256 + n_merges, ...)
+ * continues that run: train(N) == train(k) -> save -> load -> bpe_replay(k merges) -> bpe_train(N - k). */
+int bpe_replay(bpe_handle *h, const int32_t *merges, int32_t n_merges);
+
 /* ---- encode ------------------------------------------------------------------------------ */
 
 /* regex.py:92-121 (_encode_chunk per chunk, concatenated: encode_ordinary) and basic.py:57-74
@@ -197,6 +204,9 @@ int bpe_decode(bpe_handle *h, const int32_t *ids, uint64_t n_ids, const uint8_t 
  * NVLink box (peer access required).  world == 1 works without peers (tests). */
 int bpe_xchg_create(bpe_handle *h, int32_t world, int32_t rank, int32_t vocab_cap, uint8_t *ipc_handle_out /* [64] */);
 int bpe_xchg_attach(bpe_handle *h, const uint8_t *all_handles /* [world][64], own slot ignored */);
+/* Handshake over the mapped blocks (every rank calls it): push a flag to every peer, wait for theirs, pull a magic
+ * word from every peer; *ok = 1 when all of that worked within timeout_ms.  The host falls back to collectives otherwise. */
+int bpe_xchg_probe(bpe_handle *h, int32_t timeout_ms, int32_t *ok);
 /* Unmap the peers' blocks (before any rank re-creates or destroys its own: detach everywhere, synchronise the
  * ranks, then bpe_xchg_create / bpe_destroy). */
 int bpe_xchg_detach(bpe_handle *h);

@@ -125,6 +125,9 @@ struct XHdr {
     u64 dflag[XCHG_MAX_RANKS];        // dflag[r] = s+1: rank r's delta of round s is complete
     u64 cflag[XCHG_MAX_RANKS];        // cflag[r] = s+1: rank r's candidate of round s is in cand[r]
     long long cand[XCHG_MAX_RANKS];
+    u64 pflag[XCHG_MAX_RANKS];        // bpe_xchg_probe: pflag[r] = probe round rank r has reached
+    u64 magic;                        // written at creation; a peer that can read it can pull from this block
+    u64 probe_round;
 };
 static_assert(sizeof(XHdr) <= XCHG_HDR_BYTES, "exchange header must fit its slot");
 

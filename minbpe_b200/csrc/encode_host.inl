@@ -76,6 +76,74 @@ static int encode_chunks_on(bpe_handle *h, const uint8_t *bytes, uint64_t n, con
     return rc;
 }
 
+// Apply the merges in rank order to the loaded BYTE stream ("repeatedly merge the present pair with the lowest merge
+// index", regex.py:97-108, over all chunks at once) with the training kernels: select the lowest present rank, merge,
+// update the pair table incrementally.  On return the stream is the encoded text and the table equals
+// get_stats(stream) — which is also exactly the state of a training run after these merges (resume: bpe_replay).
+static int replay_merges_on(bpe_handle *h, const int32_t *merges, int32_t n_merges) {
+    int rc;
+    const u32 V = std::max(256u + (u32)n_merges, h->opt_vocab_cap);
+    if ((rc = ensure_delta(h, V))) return rc;
+    int *d_merges = nullptr;
+    CU(cudaMalloc(&d_merges, (size_t)n_merges * 8));
+    cudaError_t e = cudaMemcpyAsync(d_merges, merges, (size_t)n_merges * 8, cudaMemcpyHostToDevice, h->stream);
+    h->tm.h2d_bytes += (u64)n_merges * 8;
+    if (e != cudaSuccess) { cudaFree(d_merges); return fail(h, BPE_ERR_CUDA, cudaGetErrorString(e)); }
+    const u64 cap = auto_table_cap(h, 0);
+    if ((rc = build_table(h, cap)) || (rc = pull_ctl(h))) { cudaFree(d_merges); return rc; }
+    h->h_ctl->overflow = 0;
+    h->h_ctl->table_limit = (u64)(TABLE_MAX_LOAD * (double)cap);
+    h->h_ctl->iter = 0; h->h_ctl->done = 0; h->h_ctl->max_iter = 0xffffffffu; h->h_ctl->found_pos = POS_NONE;
+    if ((rc = push_ctl(h))) { cudaFree(d_merges); return rc; }
+    // at most one round per merge rank
+    int rounds_left = n_merges;
+    while (rounds_left > 0 && !h->h_ctl->done) {
+        const int k = std::min(h->opt_batch, rounds_left);
+        const int iters_before = (int)h->h_ctl->iter;
+        maybe_repack(h);
+        for (int i = 0; i < k; ++i) {
+            k_select_rank<<<(n_merges + 255) / 256, 256, 0, h->stream>>>(d_merges, n_merges, h->table, h->ctl);
+            k_select_rank_finish<<<1, 1, 0, h->stream>>>(d_merges, h->ctl);
+            launch_merge(h, h->delta, 0);
+            k_apply_delta<<<(h->V + 255) / 256, 256, 0, h->stream>>>(h->table, h->ctl, h->delta, h->V, 0, 0, 0, 1, 0);
+            h->tm.kernel_launches += 3;
+        }
+        if ((rc = pull_ctl(h))) { cudaFree(d_merges); return rc; }
+        if (h->h_ctl->overflow) {
+            // rounds after the overflowing one were skipped on the device: give them back
+            const int performed = (int)h->h_ctl->iter - iters_before;
+            if ((rc = handle_overflow(h))) { cudaFree(d_merges); return rc; }
+            rounds_left -= std::max(performed, 1);
+            continue;
+        }
+        rounds_left -= k;
+    }
+    cudaFree(d_merges);
+    cudaError_t le = cudaGetLastError();
+    if (le != cudaSuccess) return fail(h, BPE_ERR_CUDA, std::string("replay: ") + cudaGetErrorString(le));
+    return BPE_OK;
+}
+
+// Resume training (base.py:140-165 load() followed by more train()): bring a freshly loaded byte stream to the state
+// a training run has after `n_merges` merges, so that bpe_train(more, first_idx = 256 + n_merges) continues it.
+extern "C" int bpe_replay(bpe_handle *h, const int32_t *merges, int32_t n_merges) {
+    if (!h || n_merges < 0 || (n_merges && !merges)) return BPE_ERR_ARG;
+    if (!h->loaded || !h->bytes_only) return fail(h, BPE_ERR_STATE, "bpe_replay needs a freshly loaded byte stream");
+    CU(cudaSetDevice(h->device));
+    h->tm.kernel_launches = 0;
+    int rc = pull_ctl(h);
+    if (rc) return rc;
+    if (n_merges == 0 || h->h_ctl->n < 2) return BPE_OK;
+    if ((rc = replay_merges_on(h, merges, n_merges))) return rc;
+    // leave the control block as bpe_train expects it
+    h->h_ctl->done = 0; h->h_ctl->iter = 0; h->h_ctl->max_iter = 0; h->h_ctl->found_pos = POS_NONE;
+    if ((rc = push_ctl(h))) return rc;
+    h->table_valid = true;
+    h->bytes_only = false;
+    h->max_id = std::max(h->max_id, 255u + (u32)n_merges);
+    return BPE_OK;
+}
+
 static int encode_on(bpe_handle *h, const uint8_t *bytes, uint64_t n, const uint64_t *offs, uint64_t n_chunks,
                      const int32_t *merges, int32_t n_merges, const uint8_t *byte_perm, int32_t *out_ids,
                      uint64_t out_cap, uint64_t *out_n) {
@@ -97,47 +165,7 @@ static int encode_on(bpe_handle *h, const uint8_t *bytes, uint64_t n, const uint
     h->loaded = true; h->bytes_only = true; h->table_valid = false;
     if ((rc = pull_ctl(h))) return rc;
 
-    if (n_merges > 0 && n >= 2) {
-        const u32 V = 256u + (u32)n_merges;
-        if ((rc = ensure_delta(h, V))) return rc;
-        int *d_merges = nullptr;
-        CU(cudaMalloc(&d_merges, (size_t)n_merges * 8));
-        cudaError_t e = cudaMemcpyAsync(d_merges, merges, (size_t)n_merges * 8, cudaMemcpyHostToDevice, h->stream);
-        h->tm.h2d_bytes += (u64)n_merges * 8;
-        if (e != cudaSuccess) { cudaFree(d_merges); return fail(h, BPE_ERR_CUDA, cudaGetErrorString(e)); }
-        const u64 cap = auto_table_cap(h, 0);
-        if ((rc = build_table(h, cap)) || (rc = pull_ctl(h))) { cudaFree(d_merges); return rc; }
-        h->h_ctl->overflow = 0;
-        h->h_ctl->table_limit = (u64)(TABLE_MAX_LOAD * (double)cap);
-        h->h_ctl->iter = 0; h->h_ctl->done = 0; h->h_ctl->max_iter = 0xffffffffu; h->h_ctl->found_pos = POS_NONE;
-        if ((rc = push_ctl(h))) { cudaFree(d_merges); return rc; }
-        // at most one round per merge rank
-        int rounds_left = n_merges;
-        while (rounds_left > 0 && !h->h_ctl->done) {
-            const int k = std::min(h->opt_batch, rounds_left);
-            const int iters_before = (int)h->h_ctl->iter;
-            maybe_repack(h);
-            for (int i = 0; i < k; ++i) {
-                k_select_rank<<<(n_merges + 255) / 256, 256, 0, h->stream>>>(d_merges, n_merges, h->table, h->ctl);
-                k_select_rank_finish<<<1, 1, 0, h->stream>>>(d_merges, h->ctl);
-                launch_merge(h, h->delta, 0);
-                k_apply_delta<<<(h->V + 255) / 256, 256, 0, h->stream>>>(h->table, h->ctl, h->delta, h->V, 0, 0, 0, 1, 0);
-                h->tm.kernel_launches += 3;
-            }
-            if ((rc = pull_ctl(h))) { cudaFree(d_merges); return rc; }
-            if (h->h_ctl->overflow) {
-                // rounds after the overflowing one were skipped on the device: give them back
-                const int performed = (int)h->h_ctl->iter - iters_before;
-                if ((rc = handle_overflow(h))) { cudaFree(d_merges); return rc; }
-                rounds_left -= std::max(performed, 1);
-                continue;
-            }
-            rounds_left -= k;
-        }
-        cudaFree(d_merges);
-        cudaError_t le = cudaGetLastError();
-        if (le != cudaSuccess) return fail(h, BPE_ERR_CUDA, std::string("encode: ") + cudaGetErrorString(le));
-    }
+    if (n_merges > 0 && n >= 2 && (rc = replay_merges_on(h, merges, n_merges))) return rc;
     const u64 kept_d2h = h->tm.d2h_bytes;
     rc = bpe_read_stream(h, out_ids, out_cap, out_n);
     h->tm.d2h_bytes += kept_d2h;

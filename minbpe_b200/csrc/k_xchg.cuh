@@ -58,13 +58,36 @@ __device__ __forceinline__ void st_relaxed_sys_u64(void *p, u64 v) { asm volatil
 // after ~20 s of SM clocks the wait gives up and raises ctl->overflow = 2, which gates every later kernel of the
 // loop off; bpe_step_poll reports it.
 #define XCHG_TIMEOUT_CYCLES 40000000000ll
-__device__ __forceinline__ bool x_wait(const u64 *flag, u64 target, Ctl *ctl) {
+__device__ __forceinline__ bool x_wait_cycles(const u64 *flag, u64 target, long long cycles) {
     const long long t0 = clock64();
     u32 spins = 0;
     while (ld_acquire_sys_u64(flag) < target) {
-        if ((++spins & 0xfffu) == 0 && clock64() - t0 > XCHG_TIMEOUT_CYCLES) { ctl->overflow = 2; return false; }
+        if ((++spins & 0xfffu) == 0 && clock64() - t0 > cycles) return false;
     }
     return true;
+}
+__device__ __forceinline__ bool x_wait(const u64 *flag, u64 target, Ctl *ctl) {
+    if (x_wait_cycles(flag, target, XCHG_TIMEOUT_CYCLES)) return true;
+    ctl->overflow = 2;
+    return false;
+}
+
+// Handshake over the freshly mapped blocks (bpe_xchg_probe): every rank PUSHES a round number into every peer's
+// header and PULLS the peer's magic word, with a short timeout.  result[0] = 1 when all peers answered and every pull
+// returned the magic; the host falls back to the NCCL exchange otherwise.
+#define XCHG_MAGIC 0x6270655f78636867ull   /* "bpe_xchg" */
+__global__ void __launch_bounds__(32) k_xchg_probe(XArgs X, long long timeout_cycles, u32 *result) {
+    XHdr *me = x_hdr(X, X.rank);
+    const u64 round = me->probe_round + 1;
+    const int r = (int)threadIdx.x;
+    bool ok = true;
+    if (r < X.world) {
+        st_release_sys_u64(&x_hdr(X, r)->pflag[X.rank], round);
+        ok = x_wait_cycles(&me->pflag[r], round, timeout_cycles);
+        if (ok) ok = ld_relaxed_sys_u64(&x_hdr(X, r)->magic) == XCHG_MAGIC;
+    }
+    const bool all = __all_sync(0xffffffffu, ok);
+    if (r == 0) { me->probe_round = round; result[0] = all ? 1u : 0u; }
 }
 
 // ---- tie-break across shards (one warp) ----------------------------------------------------------

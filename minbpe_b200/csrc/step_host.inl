@@ -210,6 +210,10 @@ extern "C" int bpe_xchg_create(bpe_handle *h, int32_t world, int32_t rank, int32
     const u64 bytes = XCHG_HDR_BYTES + 2 * stride;
     CU(cudaMalloc(&h->xchg, bytes));
     CU(cudaMemset(h->xchg, 0, bytes));
+    {
+        const u64 magic = XCHG_MAGIC;
+        CU(cudaMemcpy(h->xchg + offsetof(XHdr, magic), &magic, 8, cudaMemcpyHostToDevice));
+    }
     h->xchg_bytes = bytes; h->xchg_stride = stride; h->xchg_V = (u32)vocab_cap;
     h->xargs.world = world; h->xargs.rank = rank; h->xargs.delta_stride = stride;
     h->xargs.peer[rank] = h->xchg;
@@ -246,6 +250,24 @@ extern "C" int bpe_xchg_attach(bpe_handle *h, const uint8_t *all_handles) {
         h->xargs.peer[r] = (unsigned char *)p;
     }
     h->xchg_attached = true;
+    return BPE_OK;
+}
+
+// Handshake with every mapped peer (push a flag, wait for theirs, pull their magic word) with a short timeout:
+// *ok = 1 when the peer-memory path works in both directions.  Every rank must call it (it waits for the others).
+extern "C" int bpe_xchg_probe(bpe_handle *h, int32_t timeout_ms, int32_t *ok) {
+    if (!h || !ok || timeout_ms <= 0) return BPE_ERR_ARG;
+    *ok = 0;
+    if (!h->xchg_attached) return fail(h, BPE_ERR_STATE, "bpe_xchg_probe needs bpe_xchg_create + bpe_xchg_attach");
+    CU(cudaSetDevice(h->device));
+    int khz = 1500000;
+    cudaDeviceGetAttribute(&khz, cudaDevAttrClockRate, h->device);
+    const long long cycles = (long long)timeout_ms * (long long)khz;
+    k_xchg_probe<<<1, 32, 0, h->stream>>>(h->xargs, cycles, h->d_err);
+    u32 res = 0;
+    CU(cudaMemcpyAsync(&res, h->d_err, 4, cudaMemcpyDeviceToHost, h->stream));
+    CU(cudaStreamSynchronize(h->stream));
+    *ok = (int32_t)res;
     return BPE_OK;
 }
 

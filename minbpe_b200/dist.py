@@ -112,21 +112,54 @@ class GpuStepEngine:
     # ---- exchanges over NVLink peer memory (k_xchg.cuh): no host call per merge ----
     def xchg_setup(self, world, rank, vocab_cap, group=None):
         """Create this rank's exchange block (or keep the one of the same shape), all-gather the CUDA IPC handles
-        through torch.distributed and map the peers' blocks."""
+        through torch.distributed and map the peers' blocks.  Returns True when EVERY rank succeeded (the ranks agree
+        on the answer: a local failure — no peer access, IPC refused — is exchanged, never raised between two
+        collectives); on False the caller falls back to the collective exchange."""
+        from .engine import EngineError
         key = (world, rank, vocab_cap)
         if getattr(self, "_xchg_key", None) == key:
-            return
+            return True
+        self._xchg_key = None
         if world > 1:
-            self.e.xchg_detach()                # unmap the peers' old blocks ...
+            try:
+                self.e.xchg_detach()            # unmap the peers' old blocks ...
+            except EngineError:
+                pass
             torch.cuda.synchronize(self.device)
             dist.barrier(group=group)           # ... everywhere, before any rank frees its own
-        mine = torch.from_numpy(self.e.xchg_create(world, rank, vocab_cap)).to(self.device)
+        ok, mine = 1, torch.zeros(64, dtype=torch.uint8, device=self.device)
+        try:
+            mine = torch.from_numpy(self.e.xchg_create(world, rank, vocab_cap)).to(self.device)
+        except EngineError as ex:
+            ok, self.xchg_error = 0, str(ex)
         if world > 1:
             parts = [torch.empty_like(mine) for _ in range(world)]
             dist.all_gather(parts, mine, group=group)
-            self.e.xchg_attach(torch.stack(parts).cpu().numpy())
-            dist.barrier(group=group)           # every rank has mapped every block before the first flag is written
-        self._xchg_key = key
+            flag = torch.tensor([ok], device=self.device)
+            dist.all_reduce(flag, op=dist.ReduceOp.MIN, group=group)
+            if int(flag.item()):
+                try:
+                    self.e.xchg_attach(torch.stack(parts).cpu().numpy())
+                except EngineError as ex:
+                    ok, self.xchg_error = 0, str(ex)
+            else:
+                ok = 0
+            flag = torch.tensor([ok], device=self.device)
+            dist.all_reduce(flag, op=dist.ReduceOp.MIN, group=group)   # also: every rank has mapped every block before the first flag is written
+            ok = int(flag.item())
+            if ok:      # handshake kernel: flags pushed to and magic words pulled from every peer, short timeout
+                try:
+                    ok = int(self.e.xchg_probe(3000))
+                except EngineError as ex:
+                    ok, self.xchg_error = 0, str(ex)
+                if not ok and not getattr(self, "xchg_error", None):
+                    self.xchg_error = "peer-memory handshake (bpe_xchg_probe) failed or timed out"
+                flag = torch.tensor([ok], device=self.device)
+                dist.all_reduce(flag, op=dist.ReduceOp.MIN, group=group)
+                ok = int(flag.item())
+        if ok:
+            self._xchg_key = key
+        return bool(ok)
 
     def fused(self, n_iters):
         self.e.step_fused(n_iters)
@@ -157,8 +190,10 @@ class ShardedTrainer:
         """Iteration-0 statistics: local histograms, SUM across ranks, identical tables."""
         self.num_merges, self.first_idx = num_merges, first_idx
         with self._ctx():
+            if self.exchange == "p2p" and not self.eng.xchg_setup(self.world, self.rank, first_idx + num_merges, self.group):
+                self.exchange = "collective"     # agreed by all ranks (no peer access / IPC refused): NCCL all-reduces instead
+                self.exchange_fallback = getattr(self.eng, "xchg_error", "a peer rank could not set up the exchange block")
             if self.exchange == "p2p":
-                self.eng.xchg_setup(self.world, self.rank, first_idx + num_merges, self.group)
                 if self.world > 1:   # the previous run's last round may still be read by a slower peer
                     torch.cuda.synchronize()
                     dist.barrier(group=self.group)

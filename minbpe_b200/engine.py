@@ -55,6 +55,7 @@ def load_library():
         "bpe_get_stats": ([vp, vp, vp, u64, P(u64)], ci),
         "bpe_merge": ([vp, i32, i32, i32, P(u64)], ci),
         "bpe_train": ([vp, i32, i32, vp, vp, P(i32)], ci),
+        "bpe_replay": ([vp, vp, i32], ci),
         "bpe_encode": ([vp, vp, u64, vp, u64, vp, i32, vp, vp, u64, P(u64)], ci),
         "bpe_encode_text_gpt4": ([vp, vp, u64, vp, i32, vp, vp, u64, P(u64)], ci),
         "bpe_encode_stats": ([vp, vp], ci),
@@ -77,6 +78,7 @@ def load_library():
         "bpe_xchg_create": ([vp, i32, i32, i32, vp], ci),
         "bpe_xchg_attach": ([vp, vp], ci),
         "bpe_xchg_detach": ([vp], ci),
+        "bpe_xchg_probe": ([vp, i32, P(i32)], ci),
         "bpe_step_fused": ([vp, i32], ci),
     }
     for name, (args, res) in sig.items():
@@ -175,6 +177,11 @@ class Engine:
         self._check(self._lib.bpe_train(self._h, int(num_merges), int(first_idx), _ptr(pairs), _ptr(counts),
                                         ctypes.byref(done)), "bpe_train")
         return pairs[: done.value], counts[: done.value], done.value
+
+    def replay(self, merges):
+        """Apply `merges` ([M,2] int32, rank order) to the freshly loaded byte stream; train(first_idx=256+M) then resumes."""
+        m = np.ascontiguousarray(np.asarray(merges, dtype=np.int32).reshape(-1, 2))
+        self._check(self._lib.bpe_replay(self._h, _ptr(m) if m.size else None, m.shape[0]), "bpe_replay")
 
     def encode(self, data, offsets, merges, byte_perm=None):
         """-> ids int32.  merges: [M,2] int32 in rank order (id of rank r = 256 + r)."""
@@ -315,6 +322,11 @@ class Engine:
     def xchg_attach(self, all_handles):
         a = np.ascontiguousarray(all_handles, dtype=np.uint8).reshape(-1)
         self._check(self._lib.bpe_xchg_attach(self._h, _ptr(a)), "bpe_xchg_attach")
+
+    def xchg_probe(self, timeout_ms=3000):
+        ok = ctypes.c_int32()
+        self._check(self._lib.bpe_xchg_probe(self._h, int(timeout_ms), ctypes.byref(ok)), "bpe_xchg_probe")
+        return bool(ok.value)
 
     def xchg_detach(self):
         self._check(self._lib.bpe_xchg_detach(self._h), "bpe_xchg_detach")

