@@ -441,7 +441,7 @@ def strong_leg(args, eng, rank, world, local):
     dense early merges (W..W+K) and sparse later ones (S..S+K) — plus the sha256 of the merges so far (equal lines at
     N = 1, 2, 4, 8 <=> identical merges) and a check of the first merges against the oracle's weighted loop over the
     distinct chunks of the WHOLE corpus (gathered from all ranks).  N=1 runs the single-GPU device-driven loop
-    (bpe_train), N>1 the sharded loop with the NVLink exchange kernels."""
+    (bpe_train), N>1 the sharded loop (--exchange: NCCL all-reduces by default, the NVLink peer-memory kernels opt-in)."""
     import torch
     import torch.distributed as dist
     from minbpe_b200 import engine as E
@@ -501,7 +501,7 @@ def strong_leg(args, eng, rank, world, local):
         eng.set_option(E.OPT_VOCAB_CAP, 0)
     else:
         step = GpuStepEngine(eng, local)
-        tr = ShardedTrainer(step, rank, world, poll_every=16)
+        tr = ShardedTrainer(step, rank, world, poll_every=16, exchange=args.exchange)
         tr.prepare(M)
 
         def window(k, name):
@@ -671,7 +671,8 @@ def merges_for_encode(eng, n_merges):
 def run_sharded(args, rank, world, local):
     """bench.py --gpus N>1 (one rank per GPU under torchrun).  Primary line: WEAK scaling of the cfg3-shaped loop, rank r
     holding part r of one N * size_mib corpus (parts cut at letter+space: together exactly the RegexTokenizer split of
-    the whole corpus), per-merge exchanges by our NVLink peer-memory kernels.  `strong_cfg4` = strong_leg()."""
+    the whole corpus), per-merge exchanges per --exchange (default: two NCCL all-reduces on the kernels' stream; p2p =
+    the NVLink peer-memory kernels of k_xchg.cuh).  `strong_cfg4` = strong_leg()."""
     import torch
     import torch.distributed as dist
     from minbpe_b200 import engine as E
@@ -707,7 +708,7 @@ def run_sharded(args, rank, world, local):
     t0 = time.perf_counter()
     eng.load_text_gpt4(raw)
     h2d = eng.timing()["h2d_bytes"]
-    tr = ShardedTrainer(step, rank, world, poll_every=16)
+    tr = ShardedTrainer(step, rank, world, poll_every=16, exchange=args.exchange)
     tr.prepare(W + K)
     tr.run()
     pairs_e2e, _, n_e2e = tr.result()
@@ -717,7 +718,7 @@ def run_sharded(args, rank, world, local):
 
     # ---- device-resident: W warm-up merges, then exactly K timed; stream loaded from the HOST regex split ----
     eng.load_stream(raw, offs)
-    tr = ShardedTrainer(step, rank, world, poll_every=16)
+    tr = ShardedTrainer(step, rank, world, poll_every=16, exchange=args.exchange)
     tr.prepare(W + K)
     tr.run(W)
     sync_all()
@@ -755,8 +756,11 @@ def run_sharded(args, rank, world, local):
             "vs_baseline": None, "dtype": "int32", "data": "synthetic",
             "config": {"workload": f"RegexTokenizer.train merge loop (GPT-4 split), {args.size_mib} MiB synthetic UTF-8 per GPU "
                                    f"(seed {args.seed}): rank r = part r of one {args.size_mib * world} MiB corpus, parts cut at "
-                                   f"letter+space (a provable chunk boundary), merge steps {W}..{W + K - 1}; per merge: candidate push on "
-                                   f"ties + delta pull/sum fused with the table update, over NVLink peer memory (k_xchg.cuh), no NCCL call",
+                                   f"letter+space (a provable chunk boundary), merge steps {W}..{W + K - 1}; per merge: " + (
+                                       "candidate push on ties + delta pull/sum fused with the table update, over NVLink peer memory "
+                                       "(k_xchg.cuh), no NCCL call" if tr.exchange == "p2p" else
+                                       "all-reduce MIN of the tie-break candidate (8 B) + all-reduce SUM of the statistics delta, NCCL "
+                                       "on the stream the kernels run on"),
                        "parallelism": f"shard{world}", "prep_s": round(prep_s, 1), "consistent": bool(ok),
                        "exchange_used": tr.exchange, "exchange_fallback_reason": getattr(tr, "exchange_fallback", None),
                        "shard_bytes_rank0": int(hi - lo),
@@ -1017,6 +1021,9 @@ def main():
     ap.add_argument("--encode-gb", type=float, default=4.0,
                     help="also run BASELINE configs[4] (encode this many 1e9 bytes with a 32k merges table; N GPUs = replicas over "
                          "byte-range shards) and report it as encode_cfg5; 0 = skip")
+    ap.add_argument("--exchange", default=os.environ.get("BPE_EXCHANGE", "collective"), choices=["collective", "p2p"],
+                    help="N>1: per-merge exchange of the sharded loop. collective = two NCCL all-reduces (validated on 2/4/8 B200s); "
+                         "p2p = the hand-written NVLink peer-memory kernels of k_xchg.cuh (opt-in until validated on hardware)")
     ap.add_argument("--leg-budget-s", type=int, default=900,
                     help="wall-clock budget of the optional legs (whole-loop run, cfg4, cfg5) after the contract line is complete; "
                          "when it runs out the line is printed with the legs finished so far")

@@ -170,13 +170,17 @@ class ShardedTrainer:
     rank's shard (Engine.load_stream)."""
 
     def __init__(self, eng, rank=None, world=None, group=None, poll_every=16, exchange=None):
-        """exchange: "p2p" = our kernels over NVLink peer memory (k_xchg.cuh; the default for a GPU engine),
-        "collective" = two torch.distributed all-reduces per merge (NCCL / gloo; the CPU tests' stand-in engine)."""
+        """exchange: "collective" = two torch.distributed all-reduces per merge (NCCL / gloo) — the default: it is the
+        path that has been validated on 2/4/8 B200s; "p2p" = our kernels over NVLink peer memory (k_xchg.cuh), opt-in
+        (argument, or BPE_EXCHANGE=p2p) until it has run on multi-GPU hardware."""
         self.eng, self.group = eng, group
         self.rank = dist.get_rank(group) if rank is None else rank
         self.world = dist.get_world_size(group) if world is None else world
         self.poll_every = poll_every
-        self.exchange = exchange or ("p2p" if hasattr(eng, "xchg_setup") else "collective")
+        want = exchange or os.environ.get("BPE_EXCHANGE", "collective")
+        if want not in ("p2p", "collective"):
+            raise ValueError(f"exchange must be 'p2p' or 'collective', not {want!r}")
+        self.exchange = want if hasattr(eng, "xchg_setup") else "collective"
 
     def _allreduce(self, t, op):
         if self.world > 1:
