@@ -1,6 +1,8 @@
 // common.cuh — shared definitions for the sm_100a BPE kernels.
 #pragma once
+#ifndef BPE_SIMT_EMU
 #include <cuda_runtime.h>
+#endif
 #include <stdint.h>
 
 typedef uint32_t u32;
@@ -138,6 +140,7 @@ __device__ __forceinline__ ull *x_local_delta(const unsigned char *xbase, u64 de
 }
 
 // ---- small helpers -------------------------------------------------------------------------
+#ifndef BPE_SIMT_EMU
 __device__ __forceinline__ u64 ld_volatile_u64(const u64 *p) {
     u64 v;
     asm volatile("ld.volatile.global.u64 %0, [%1];" : "=l"(v) : "l"(p));
@@ -151,8 +154,10 @@ __device__ __forceinline__ u32 ld_volatile_u32(const u32 *p) {
     asm volatile("ld.volatile.global.u32 %0, [%1];" : "=r"(v) : "l"(p));
     return v;
 }
+#endif
 __device__ __forceinline__ u32 lane_id() { return threadIdx.x & 31; }
 
+#ifndef BPE_SIMT_EMU
 // ---- mbarrier + bulk async copy (TMA 1-D) — hand-written PTX for sm_100a ---------------------
 __device__ __forceinline__ u32 smem_addr(const void *p) { return (u32)__cvta_generic_to_shared(p); }
 
@@ -161,49 +166,10 @@ __device__ __forceinline__ void mbar_init(u64 *bar, u32 count) {
 }
 // make mbarrier initialisation visible to the async proxy before the first bulk copy targets it
 __device__ __forceinline__ void fence_mbar_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+// ordinary shared-memory stores before a bulk copy that overwrites the same bytes
+__device__ __forceinline__ void fence_proxy_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 
-__device__ __forceinline__ void mbar_arrive_expect_tx(u64 *bar, u32 tx_bytes) {
-    u64 state;
-    asm volatile("mbarrier.arrive.expect_tx.release.cta.shared::cta.b64 %0, [%1], %2;"
-                 : "=l"(state) : "r"(smem_addr(bar)), "r"(tx_bytes) : "memory");
-    (void)state;
-}
-__device__ __forceinline__ bool mbar_try_wait(u64 *bar, u32 parity) {
-    u32 ok;
-    asm volatile("{\n\t.reg .pred P;\n\t"
-                 "mbarrier.try_wait.parity.shared::cta.b64 P, [%1], %2;\n\t"
-                 "selp.b32 %0, 1, 0, P;\n\t}"
-                 : "=r"(ok) : "r"(smem_addr(bar)), "r"(parity) : "memory");
-    return ok != 0;
-}
-// try_wait with a suspend-time hint: the thread sleeps in hardware until the phase completes (or
-// `ns` elapse) instead of burning issue slots in a polling loop; wake-up on completion is immediate
-__device__ __forceinline__ bool mbar_try_wait_hint(u64 *bar, u32 parity, u32 ns) {
-    u32 ok;
-    asm volatile("{\n\t.reg .pred P;\n\t"
-                 "mbarrier.try_wait.parity.shared::cta.b64 P, [%1], %2, %3;\n\t"
-                 "selp.b32 %0, 1, 0, P;\n\t}"
-                 : "=r"(ok) : "r"(smem_addr(bar)), "r"(parity), "r"(ns) : "memory");
-    return ok != 0;
-}
-__device__ __forceinline__ void mbar_wait(u64 *bar, u32 parity) { while (!mbar_try_wait_hint(bar, parity, 20000u)) {} }
-__device__ __forceinline__ void mbar_arrive(u64 *bar) {
-    u64 state;
-    asm volatile("mbarrier.arrive.release.cta.shared::cta.b64 %0, [%1];" : "=l"(state) : "r"(smem_addr(bar)) : "memory");
-    (void)state;
-}
-// barrier among a subset of the CTA's warps (id 1..15; id 0 is __syncthreads)
-__device__ __forceinline__ void named_bar_sync(u32 id, u32 nthreads) {
-    asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
-}
-
-// global -> shared bulk copy (SASS: UBLKCP); bytes, src and dst must be multiples of 16
-__device__ __forceinline__ void bulk_g2s(void *dst_smem, const void *src_gmem, u32 bytes, u64 *bar) {
-    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
-                 ::"r"(smem_addr(dst_smem)), "l"(src_gmem), "r"(bytes), "r"(smem_addr(bar)) : "memory");
-}
-
-// ---- the same with 32-bit shared-window addresses kept in registers.  Generic pointers into dynamic
+// ---- shared memory through 32-bit shared-window addresses kept in registers.  Generic pointers into dynamic
 //      shared memory make the compiler rebuild the window base (S2R SR_CgaCtaId + LEA) and the index
 //      arithmetic in front of every access; the merge kernel's inner loop addresses shared memory
 //      explicitly instead. ----
@@ -235,6 +201,8 @@ __device__ __forceinline__ void mbar_arrive_expect_tx_a(u32 bar_a, u32 tx_bytes)
     asm volatile("mbarrier.arrive.expect_tx.release.cta.shared::cta.b64 %0, [%1], %2;" : "=l"(state) : "r"(bar_a), "r"(tx_bytes) : "memory");
     (void)state;
 }
+// try_wait with a suspend-time hint: the thread sleeps in hardware until the phase completes (or 20 us elapse)
+// instead of burning issue slots in a polling loop; wake-up on completion is immediate
 __device__ __forceinline__ void mbar_wait_a(u32 bar_a, u32 parity) {
     u32 ok;
     do {
@@ -244,7 +212,45 @@ __device__ __forceinline__ void mbar_wait_a(u32 bar_a, u32 parity) {
                      : "=r"(ok) : "r"(bar_a), "r"(parity), "r"(20000u) : "memory");
     } while (!ok);
 }
+// global -> shared bulk copy (SASS: UBLKCP); bytes, src and dst must be multiples of 16
 __device__ __forceinline__ void bulk_g2s_a(u32 dst_a, const void *src_gmem, u32 bytes, u32 bar_a) {
     asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
                  ::"r"(dst_a), "l"(src_gmem), "r"(bytes), "r"(bar_a) : "memory");
 }
+
+#else  // BPE_SIMT_EMU ================================================================================
+// The same helpers for the CPU SIMT emulator (tests/emu/cuda_emu.h — test infrastructure, never part of
+// libb200bpe.so): polling loads yield to the other emulated threads, "shared-window addresses" are byte
+// offsets into the block's dynamic shared memory, a bulk copy completes at issue, and the mbarrier word keeps
+// {outstanding bytes, pending arrivals, phase} with the PTX phase/parity semantics.
+static inline u64 ld_volatile_u64(const u64 *p) { emu::spin(); return __atomic_load_n(p, __ATOMIC_ACQUIRE); }
+static inline void st_volatile_u64(u64 *p, u64 v) { __atomic_store_n(p, v, __ATOMIC_RELEASE); }
+static inline u32 ld_volatile_u32(const u32 *p) { emu::spin(); return __atomic_load_n(p, __ATOMIC_ACQUIRE); }
+static inline char *emu_smem() { return reinterpret_cast<char *>(emu::dyn_smem()); }
+static inline u32 smem_addr(const void *p) { return (u32)(reinterpret_cast<const char *>(p) - emu_smem()); }
+struct EmuMbar { int tx; unsigned char pending, init; unsigned short phase; };
+static_assert(sizeof(EmuMbar) == 8, "one mbarrier word");
+static inline void emu_mbar_check(EmuMbar *m) { if (m->pending == 0 && m->tx == 0) { m->phase ^= 1u; m->pending = m->init; } }
+static inline void mbar_init(u64 *bar, u32 count) { EmuMbar *m = reinterpret_cast<EmuMbar *>(bar); m->tx = 0; m->pending = m->init = (unsigned char)count; m->phase = 0; }
+static inline void fence_mbar_init() {}
+static inline void fence_proxy_async_smem() {}
+static inline u32 lds32(u32 addr) { return *reinterpret_cast<u32 *>(emu_smem() + addr); }
+template <int OFF> static inline u32 lds32o(u32 addr) { return *reinterpret_cast<u32 *>(emu_smem() + addr + OFF); }
+template <int OFF> static inline uint4 lds128o(u32 addr) { return *reinterpret_cast<uint4 *>(emu_smem() + addr + OFF); }
+static inline void sts32(u32 addr, u32 v) { *reinterpret_cast<u32 *>(emu_smem() + addr) = v; }
+template <int OFF> static inline void sts32o(u32 addr, u32 v) { *reinterpret_cast<u32 *>(emu_smem() + addr + OFF) = v; }
+static inline void sts128(u32 addr, u32 x, u32 y, u32 z, u32 w) { *reinterpret_cast<uint4 *>(emu_smem() + addr) = make_uint4(x, y, z, w); }
+static inline void mbar_arrive_expect_tx_a(u32 bar_a, u32 tx_bytes) {
+    EmuMbar *m = reinterpret_cast<EmuMbar *>(emu_smem() + bar_a);
+    m->tx += (int)tx_bytes; m->pending -= 1; emu_mbar_check(m);
+}
+static inline void mbar_wait_a(u32 bar_a, u32 parity) {
+    const EmuMbar *m = reinterpret_cast<const EmuMbar *>(emu_smem() + bar_a);
+    while ((u32)(m->phase & 1u) == parity) emu::spin();      // the phase with this parity has not completed yet
+}
+static inline void bulk_g2s_a(u32 dst_a, const void *src_gmem, u32 bytes, u32 bar_a) {
+    memcpy(emu_smem() + dst_a, src_gmem, bytes);
+    EmuMbar *m = reinterpret_cast<EmuMbar *>(emu_smem() + bar_a);
+    m->tx -= (int)bytes; emu_mbar_check(m);
+}
+#endif

@@ -45,8 +45,6 @@
 static_assert(SEG_TOKENS == 512, "k_merge_seg: a lane owns 4 rows x 4 tokens of a 512-token segment");
 static_assert((MS_SW * 4) % 16 == 0 && (MS_WARP_WORDS * 4) % 16 == 0, "bulk-copy destinations must stay 16-byte aligned");
 
-__device__ __forceinline__ void fence_proxy_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
-
 // delta[idx] += 1 through a CTA-private shared-memory cache: the same few neighbour ids are hit by
 // almost every merge of a dense iteration (global same-address atomics serialise in L2); the
 // persistent CTA folds them here and flushes once at exit.

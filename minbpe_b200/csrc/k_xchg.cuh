@@ -41,6 +41,7 @@ __device__ __forceinline__ ull *x_delta(const XArgs &X, int r, u32 parity) {
     return reinterpret_cast<ull *>(X.peer[r] + XCHG_HDR_BYTES + (u64)parity * X.delta_stride);
 }
 
+#ifndef BPE_SIMT_EMU
 __device__ __forceinline__ void st_release_sys_u64(u64 *p, u64 v) { asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory"); }
 __device__ __forceinline__ u64 ld_acquire_sys_u64(const u64 *p) {
     u64 v;
@@ -53,6 +54,12 @@ __device__ __forceinline__ u64 ld_relaxed_sys_u64(const void *p) {
     return v;
 }
 __device__ __forceinline__ void st_relaxed_sys_u64(void *p, u64 v) { asm volatile("st.relaxed.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory"); }
+#else   // CPU SIMT emulator (tests/emu): peers are other OS threads, system-scope accesses are C++ atomics
+static inline void st_release_sys_u64(u64 *p, u64 v) { __atomic_store_n(p, v, __ATOMIC_RELEASE); }
+static inline u64 ld_acquire_sys_u64(const u64 *p) { emu::spin(); return __atomic_load_n(p, __ATOMIC_ACQUIRE); }
+static inline u64 ld_relaxed_sys_u64(const void *p) { return __atomic_load_n(reinterpret_cast<const u64 *>(p), __ATOMIC_RELAXED); }
+static inline void st_relaxed_sys_u64(void *p, u64 v) { __atomic_store_n(reinterpret_cast<u64 *>(p), v, __ATOMIC_RELAXED); }
+#endif
 
 // Wait until *flag >= target.  A peer that died would leave this kernel spinning for ever and the GPU wedged:
 // after ~20 s of SM clocks the wait gives up and raises ctl->overflow = 2, which gates every later kernel of the
