@@ -161,6 +161,11 @@ class GpuStepEngine:
             self._xchg_key = key
         return bool(ok)
 
+    def sync_ranks(self, group=None):
+        """Every rank's queued work is done (device sync), on every rank (barrier)."""
+        torch.cuda.synchronize(self.device)
+        dist.barrier(group=group)
+
     def fused(self, n_iters):
         self.e.step_fused(n_iters)
 
@@ -197,10 +202,8 @@ class ShardedTrainer:
             if self.exchange == "p2p" and not self.eng.xchg_setup(self.world, self.rank, first_idx + num_merges, self.group):
                 self.exchange = "collective"     # agreed by all ranks (no peer access / IPC refused): NCCL all-reduces instead
                 self.exchange_fallback = getattr(self.eng, "xchg_error", "a peer rank could not set up the exchange block")
-            if self.exchange == "p2p":
-                if self.world > 1:   # the previous run's last round may still be read by a slower peer
-                    torch.cuda.synchronize()
-                    dist.barrier(group=self.group)
+            if self.exchange == "p2p" and self.world > 1:
+                self.eng.sync_ranks(self.group)   # the previous run's last round may still be read by a slower peer
             dense = self.eng.new_i64(65536)
             self.eng.begin(dense)
             self._allreduce(dense, dist.ReduceOp.SUM)     # the one collective of the run (512 KB, iteration 0)

@@ -1,5 +1,7 @@
 """GPU: the memoised chunk encode (k_encode2.cuh) — bpe_encode_text_gpt4 (split + encode on the device) and
 bpe_encode with host offsets — against the oracle's restatement of regex.py:92-121 (oracle.c_encode), bit-exact ids."""
+import os
+
 import numpy as np
 import pytest
 import regex
@@ -7,6 +9,7 @@ import regex
 import oracle
 
 pytestmark = pytest.mark.gpu
+SMALL = bool(os.environ.get("BPE_TEST_SMALL"))    # set by tests/test_emu.py: the same tests on the CPU SIMT emulator, smaller table
 
 GPT4 = regex.compile(
     r"""'(?i:[sdmt]|ll|ve|re)|[^\r\n\p{L}\p{N}]?+\p{L}+|\p{N}{1,3}| ?[^\s\p{L}\p{N}]++[\r\n]*|\s*[\r\n]|\s+(?!\S)|\s+""")
@@ -24,11 +27,12 @@ def eng():
 def trained(eng):
     """merges from 4 MiB of the synthetic corpus (600 merges) + its text"""
     from minbpe_b200.synth import generate
-    text = generate(1337, 4 << 20).tobytes().decode("utf-8")
+    n_merges = 250 if SMALL else 600
+    text = generate(1337, (1 if SMALL else 4) << 20).tobytes().decode("utf-8")
     data, offs = oracle.split_to_stream(text, GPT4)
     eng.load_stream(data, offs)
-    merges, _, done = eng.train(600)
-    assert done == 600
+    merges, _, done = eng.train(n_merges)
+    assert done == n_merges
     return text, merges
 
 
