@@ -76,8 +76,51 @@ def measured_peak():
     return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
 
 
+# Test hook: tests/test_emu.py runs this file end to end (all legs, N = 1 and 2 ranks over gloo, tiny sizes) against the
+# CPU SIMT emulator build of the library (tests/emu/), to execute the control flow of every leg in a container without a
+# GPU.  Nothing below is timed meaningfully in that mode; the driver never sets the variable.
+EMU = bool(os.environ.get("BPE_BENCH_EMU"))
+
+
+class _HostEvent:
+    def record(self, stream=None):
+        self.t = time.perf_counter()
+
+    def elapsed_time(self, other):
+        return (other.t - self.t) * 1e3
+
+
+def dev_sync():
+    if not EMU:
+        import torch
+        torch.cuda.synchronize()
+
+
+def new_event():
+    if EMU:
+        return _HostEvent()
+    import torch
+    return torch.cuda.Event(enable_timing=True)
+
+
+def dev_tensor(values, dtype=None):
+    import torch
+    return torch.tensor(values, device="cpu" if EMU else "cuda", dtype=dtype)
+
+
+def make_step_engine(eng, local):
+    if EMU:
+        sys.path.insert(0, os.path.join(ROOT, "tests", "emu"))
+        from host_step import HostStepEngine
+        return HostStepEngine(eng)
+    from minbpe_b200.dist import GpuStepEngine
+    return GpuStepEngine(eng, local)
+
+
 def pin_host(arr):
     """cudaHostRegister the numpy buffer (the contract's "pinned host memory"); False if refused."""
+    if EMU:
+        return False
     import torch
     try:
         rc = torch.cuda.cudart().cudaHostRegister(arr.ctypes.data, arr.nbytes, 0)
@@ -314,15 +357,14 @@ def full_run(eng, raw, offs, merges, check=True):
     """BASELINE configs[2] to completion: bpe_load_text_gpt4 + bpe_train(all merges) from the host text, then every
     merge and count compared with the oracle's weighted loop over the distinct chunks of the host `regex` split
     (oracle.c_dedup_chunks + c_train(weights): same dict as regex.py:51-54 builds, tests/test_oracle.py)."""
-    import torch
     from minbpe_b200 import engine as E
     eng.set_option(E.OPT_KERNEL_TIMING, 0)
-    torch.cuda.synchronize()
+    dev_sync()
     t0 = time.perf_counter()
     eng.load_text_gpt4(raw)
     t_load = time.perf_counter() - t0
     pairs, counts, done = eng.train(merges)
-    torch.cuda.synchronize()
+    dev_sync()
     t_all = time.perf_counter() - t0
     tm = eng.timing()
     peak, _ = measured_peak()
@@ -442,11 +484,10 @@ def strong_leg(args, eng, rank, world, local):
     N = 1, 2, 4, 8 <=> identical merges) and a check of the first merges against the oracle's weighted loop over the
     distinct chunks of the WHOLE corpus (gathered from all ranks).  N=1 runs the single-GPU device-driven loop
     (bpe_train), N>1 the sharded loop (--exchange: NCCL all-reduces by default, the NVLink peer-memory kernels opt-in)."""
-    import torch
     import torch.distributed as dist
     from minbpe_b200 import engine as E
-    from minbpe_b200.dist import GpuStepEngine, ShardedTrainer
-    total = args.strong_gib << 30
+    from minbpe_b200.dist import ShardedTrainer
+    total = (args.strong_mib << 20) if args.strong_mib else (args.strong_gib << 30)
     vocab = args.strong_vocab
     M = vocab - 256
     K, W, S = args.steps, args.warmup, args.strong_sparse_at
@@ -456,22 +497,23 @@ def strong_leg(args, eng, rank, world, local):
     gen_s = time.time() - t0
 
     def sync():
-        torch.cuda.synchronize()
+        dev_sync()
         if world > 1:
             dist.barrier()
-            torch.cuda.synchronize()
+            dev_sync()
 
     def tmax(x):
         if world == 1:
             return x
-        t = torch.tensor([x], device="cuda", dtype=torch.float64)
+        import torch
+        t = dev_tensor([x], dtype=torch.float64)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         return float(t.item())
 
     sync()
     t0 = time.perf_counter()
     eng.load_text_gpt4(raw)
-    torch.cuda.synchronize()
+    dev_sync()
     load_s = tmax(time.perf_counter() - t0)
     eng.set_option(E.OPT_KERNEL_TIMING, 0)
     windows = {}
@@ -484,7 +526,7 @@ def strong_leg(args, eng, rank, world, local):
             nonlocal done_total
             if k <= 0:
                 return
-            torch.cuda.synchronize()
+            dev_sync()
             p, c, d = eng.train(k, first_idx=256 + done_total)
             tm = eng.timing()
             assert d == k, "corpus ran out of pairs"
@@ -500,13 +542,13 @@ def strong_leg(args, eng, rank, world, local):
         pairs = np.concatenate(all_pairs)
         eng.set_option(E.OPT_VOCAB_CAP, 0)
     else:
-        step = GpuStepEngine(eng, local)
+        step = make_step_engine(eng, local)
         tr = ShardedTrainer(step, rank, world, poll_every=16, exchange=args.exchange)
         tr.prepare(M)
 
         def window(k, name):
             sync()
-            ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            ev0, ev1 = new_event(), new_event()
             first = tr.done
             ev0.record(step.stream)
             tr.run(k)
@@ -544,13 +586,14 @@ def strong_leg(args, eng, rank, world, local):
         except Exception:  # noqa: BLE001
             pass
         sync()
-    out = {"workload": f"BASELINE configs[3]: RegexTokenizer.train, {args.strong_gib} GiB synthetic UTF-8 (seed 1338), vocab {vocab}, "
+    out = {"workload": f"BASELINE configs[3]: RegexTokenizer.train, {total / (1 << 30):g} GiB synthetic UTF-8 (seed 1338), vocab {vocab}, "
                        f"{world} GPU(s), contiguous byte-range shards cut at letter+space", "scaling": "strong",
            "bytes_total": total, "bytes_this_rank": int(hi - lo), "vocab": vocab, "delta_vector_bytes": (2 * vocab + 1) * 8,
            "exchange": "none (1 GPU)" if world == 1 else (
                "NVLink peer memory kernels (k_xchg_cand on ties + k_xchg_apply), no NCCL per merge" if exchange_used == "p2p" else
-               "torch.distributed all-reduce MIN + SUM per merge (fallback: " + str(exchange_fallback) + ")"),
-           "nvlink_pull_bytes_per_merge_per_rank": 0 if world == 1 else (world - 1) * (2 * vocab + 1) * 8,
+               "NCCL all-reduce MIN (8 B) + SUM (delta vector) per merge, on the kernels' stream" +
+               (f" (p2p was requested; fell back: {exchange_fallback})" if exchange_fallback else "")),
+           "exchanged_bytes_per_merge_per_rank": 0 if world == 1 else (2 * vocab + 1) * 8 + 8,
            "generate_s": round(gen_s, 1), "load_seconds": load_s, "windows": windows,
            "merges_sha16": merges_sha(pairs), "merges_in_sha": int(len(pairs)), "parity_vs_oracle": parity}
     return out
@@ -568,12 +611,13 @@ def encode_leg(args, eng, rank, world, merges):
     import oracle
     from minbpe_b200 import engine as E
     from minbpe_b200.dist import first_safe_cut
-    total = int(args.encode_gb * 1e9) // (1 << 20) * (1 << 20)
+    total = max(1, int(args.encode_gb * 1e9) // (1 << 20)) * (1 << 20)
     threads = max(1, host_cores() // world)
     raw, lo, hi = corpus_shard(1339, total, rank, world, threads)
     raw = np.ascontiguousarray(raw)
     pinned = pin_host(raw)
-    out = np.empty(raw.size // 2 + 1024, dtype=np.int32)     # ids: at most one per byte, ~0.3 per byte in practice
+    # ids: at most one per byte; a 32k-entry table leaves ~0.22 per byte of this corpus (room for 0.5), a small table more
+    out = np.empty((raw.size // 2 if len(merges) >= 8192 else raw.size) + 1024, dtype=np.int32)
     pin_host(out)
     eng.set_option(E.OPT_KERNEL_TIMING, 0)
     wcut = min(raw.size, 64 << 20)
@@ -582,7 +626,7 @@ def encode_leg(args, eng, rank, world, merges):
     ids = eng.encode_text_gpt4(raw[:wcut], merges, out=out)    # warm-up: tables, allocations (the memo stays warm, as for a user)
     runs = []
     for _ in range(3):
-        torch.cuda.synchronize()
+        dev_sync()
         if world > 1:
             dist.barrier()
         t0 = time.perf_counter()
@@ -597,7 +641,7 @@ def encode_leg(args, eng, rank, world, merges):
     split_ms = eng.timing()["init_ms"]
     eng.set_option(E.OPT_KERNEL_TIMING, 0)
     enc_s = st["kernel_us"] / 1e6
-    tt = torch.tensor([t, enc_s, split_ms / 1e3, float(raw.size), float(ids.size)], device="cuda", dtype=torch.float64)
+    tt = dev_tensor([t, enc_s, split_ms / 1e3, float(raw.size), float(ids.size)], dtype=torch.float64)
     if world > 1:
         mx = tt.clone(); dist.all_reduce(mx, op=dist.ReduceOp.MAX)
         sm = tt.clone(); dist.all_reduce(sm, op=dist.ReduceOp.SUM)
@@ -609,7 +653,9 @@ def encode_leg(args, eng, rank, world, merges):
         peak, _ = measured_peak()
         # parity + CPU baseline on a slice of rank 0's shard, cut where chunking cannot differ
         # (single-process regex: this process holds pinned host buffers and a CUDA context — no fork() from here)
-        cut = (16 << 20) + max(0, first_safe_cut(raw[16 << 20: (16 << 20) + (1 << 20)]))
+        cut = min(raw.size, 16 << 20)
+        if cut < raw.size:
+            cut += max(0, first_safe_cut(raw[cut: cut + (1 << 20)]))
         from minbpe_b200.presplit import chunk_offsets_1proc
         import regex
         o2 = chunk_offsets_1proc(regex.compile(GPT4), raw[:cut].tobytes())
@@ -625,7 +671,9 @@ def encode_leg(args, eng, rank, world, merges):
                 tokr = ref.RegexTokenizer()
                 tokr.merges = {(int(a), int(b)): 256 + i for i, (a, b) in enumerate(np.asarray(merges).tolist())}
                 tokr.vocab = tokr._build_vocab()
-                c2 = (1 << 20) + max(0, first_safe_cut(raw[1 << 20: (1 << 20) + (1 << 16)]))
+                c2 = min(raw.size, 1 << 20)
+                if c2 < raw.size:
+                    c2 += max(0, first_safe_cut(raw[c2: c2 + (1 << 16)]))
                 txt = raw[:c2].tobytes().decode("utf-8")
                 t0 = time.perf_counter(); rid = tokr.encode_ordinary(txt); pdt = time.perf_counter() - t0
                 py = {"value": c2 / pdt / 1e9, "unit": "GB/s", "cores": 1, "kind": "reference", "seconds": pdt,
@@ -652,18 +700,15 @@ def encode_leg(args, eng, rank, world, merges):
                                 "python_reference": py},
                "parity": {"equal": same, "ids_checked": int(want.size), "how": "ids of the first slice == oracle.c_encode(host regex split of that slice)"}}
     if pinned:
-        try:
-            torch.cuda.cudart().cudaHostUnregister(raw.ctypes.data)
-            torch.cuda.cudart().cudaHostUnregister(out.ctypes.data)
-        except Exception:  # noqa: BLE001
-            pass
+        unpin_host(raw)
+        unpin_host(out)
     return res
 
 
-def merges_for_encode(eng, n_merges):
+def merges_for_encode(eng, n_merges, train_mib=256):
     """A trained table for the encode leg when the run has none yet: RegexTokenizer.train on 256 MiB of the cfg3 corpus."""
     from minbpe_b200.synth import generate
-    eng.load_text_gpt4(generate(1337, 256 << 20))
+    eng.load_text_gpt4(generate(1337, train_mib << 20))
     p, _, d = eng.train(n_merges)
     return p[:d]
 
@@ -676,7 +721,7 @@ def run_sharded(args, rank, world, local):
     import torch
     import torch.distributed as dist
     from minbpe_b200 import engine as E
-    from minbpe_b200.dist import GpuStepEngine, ShardedTrainer
+    from minbpe_b200.dist import ShardedTrainer
     from minbpe_b200.presplit import chunk_offsets
     size = args.size_mib << 20
     K, W = args.steps, args.warmup
@@ -686,20 +731,23 @@ def run_sharded(args, rank, world, local):
     offs = chunk_offsets(GPT4, raw, workers=threads)      # host `regex` split of the shard: cross-checks the device splitter
     prep_s = time.time() - t0
 
-    torch.cuda.set_device(local)
-    dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    if EMU:
+        dist.init_process_group("gloo")
+    else:
+        torch.cuda.set_device(local)
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     eng = E.Engine(local)
     eng.set_option(E.OPT_KERNEL_TIMING, 1)
-    step = GpuStepEngine(eng, local)
+    step = make_step_engine(eng, local)
     sampler = None
     if rank == 0:
         sampler = ClockSampler(local)
         sampler.start()
 
     def sync_all():
-        torch.cuda.synchronize()
+        dev_sync()
         dist.barrier()
-        torch.cuda.synchronize()
+        dev_sync()
 
     # ---- e2e: host buffers -> merges through the C ABI (device split + sharded loop), wall clock, max over ranks ----
     pinned = pin_host(raw)
@@ -713,7 +761,7 @@ def run_sharded(args, rank, world, local):
     tr.run()
     pairs_e2e, _, n_e2e = tr.result()
     sync_all()
-    t_e2e = torch.tensor([time.perf_counter() - t0], device="cuda")
+    t_e2e = dev_tensor([time.perf_counter() - t0])
     dist.all_reduce(t_e2e, op=dist.ReduceOp.MAX)
 
     # ---- device-resident: W warm-up merges, then exactly K timed; stream loaded from the HOST regex split ----
@@ -724,7 +772,7 @@ def run_sharded(args, rank, world, local):
     sync_all()
     if sampler:
         sampler.begin()
-    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    ev0, ev1 = new_event(), new_event()
     eng.timing()
     ev0.record(step.stream)
     t0 = time.perf_counter()
@@ -735,12 +783,12 @@ def run_sharded(args, rank, world, local):
     if sampler:
         sampler.end()
     clocks = sampler.stop() if sampler else None
-    t_loop = torch.tensor([ev0.elapsed_time(ev1) / 1e3], device="cuda")
+    t_loop = dev_tensor([ev0.elapsed_time(ev1) / 1e3])
     dist.all_reduce(t_loop, op=dist.ReduceOp.MAX)
     pairs, counts, n = tr.result()
     tm = eng.timing()
     ok = (n == W + K) and np.array_equal(pairs[: W + K], pairs_e2e)
-    merge_ms = torch.tensor([tm["merge_kernel_ms"] / max(n, 1)], device="cuda")   # CUDA events around the merge launches, all W+K steps
+    merge_ms = dev_tensor([tm["merge_kernel_ms"] / max(n, 1)])   # CUDA events around the merge launches, all W+K steps
     merge_all = [torch.zeros_like(merge_ms) for _ in range(world)]
     dist.all_gather(merge_all, merge_ms)
     line = None
@@ -773,11 +821,10 @@ def run_sharded(args, rank, world, local):
                           "select_exchange_apply": k_ms - max(float(x.item()) for x in merge_all),
                           "how": "merge = CUDA events around the merge launches (every rank); the rest of the step = arg-max, tie filter, "
                                  "first-occurrence scan, candidate exchange, delta exchange + table update, and waiting for the slowest rank"},
-            "exchange": {"kind": "NVLink peer memory (CUDA IPC), hand-written kernels" if tr.exchange == "p2p" else
-                                 "torch.distributed all-reduce MIN + SUM per merge (fallback: " + str(getattr(tr, "exchange_fallback", None)) + ")",
-                         "delta_vector_bytes": (2 * V + 1) * 8,
-                         "nvlink_pull_bytes_per_merge_per_rank": (world - 1) * (2 * V + 1) * 8,
-                         "candidate_push_bytes_per_tie_per_rank": (world - 1) * 16},
+            "exchange": {"kind": "NVLink peer memory (CUDA IPC), hand-written kernels (k_xchg.cuh)" if tr.exchange == "p2p" else
+                                 "NCCL all-reduce MIN (8 B candidate) + SUM (delta vector) per merge, issued on the kernels' stream" +
+                                 (f" (p2p was requested; fell back: {tr.exchange_fallback})" if getattr(tr, "exchange_fallback", None) else ""),
+                         "delta_vector_bytes": (2 * V + 1) * 8},
             "roofline": {"bound": "hbm", "kernel": "k_merge_seg (rank 0; rate over the whole step incl. exchanges)",
                          "achieved": bytes_per_launch / (k_ms / 1e3) / 1e9, "peak": peak, "unit": "GB/s",
                          "frac": bytes_per_launch / (k_ms / 1e3) / 1e9 / peak, "traffic": None, "peak_source": peak_src, "ms_per_launch": k_ms},
@@ -795,8 +842,8 @@ def run_sharded(args, rank, world, local):
     dog.arm(line)
     if pinned:
         unpin_host(raw)
-    strong = guarded("strong_cfg4", strong_leg, args, eng, rank, world, local) if args.strong_gib > 0 else None
-    enc = guarded("encode_cfg5", lambda: encode_leg(args, eng, rank, world, merges_for_encode(eng, 32512))) if args.encode_gb > 0 else None
+    strong = guarded("strong_cfg4", strong_leg, args, eng, rank, world, local) if (args.strong_gib > 0 or args.strong_mib > 0) else None
+    enc = guarded("encode_cfg5", lambda: encode_leg(args, eng, rank, world, merges_for_encode(eng, args.encode_merges, args.encode_train_mib))) if args.encode_gb > 0 else None
     dog.disarm()
     if rank == 0:
         line["strong_cfg4"], line["encode_cfg5"] = strong, enc
@@ -839,7 +886,8 @@ def run_ours(args):
                "merges_per_s": done / dt, "python_reference": python_reference_run(raw)}
 
     from minbpe_b200 import engine as E
-    torch.cuda.set_device(local)
+    if not EMU:
+        torch.cuda.set_device(local)
     eng = E.Engine(local)
     eng.set_option(E.OPT_KERNEL_TIMING, 1)
 
@@ -850,7 +898,7 @@ def run_ours(args):
     # untimed warm-up of the same calls (class tables, first-touch of the big device allocations, clocks)
     eng.load_text_gpt4(raw)
     eng.train(W)
-    torch.cuda.synchronize()
+    dev_sync()
     e2e_runs = []
     for _ in range(3):   # the wall clock of a 0.2 s region is noisy (allocator, PCIe): report the median run
         t0 = time.perf_counter()
@@ -858,7 +906,7 @@ def run_ours(args):
         load_tm = eng.timing()
         t_load = time.perf_counter() - t0
         pairs_e2e, _, done = eng.train(W + K)
-        torch.cuda.synchronize()
+        dev_sync()
         e2e_runs.append((time.perf_counter() - t0, t_load))
         assert done == W + K, "corpus ran out of pairs"
     tm_e2e = eng.timing()
@@ -869,11 +917,11 @@ def run_ours(args):
     # ---- device-resident: W warm-up steps, then exactly K timed steps ----
     eng.load_stream(raw, offs)
     eng.train(W)
-    torch.cuda.synchronize()
+    dev_sync()
     sampler.begin()
     t0 = time.perf_counter()
     pairs, counts, done = eng.train(K, first_idx=256 + W)
-    torch.cuda.synchronize()
+    dev_sync()
     wall = time.perf_counter() - t0
     sampler.end()
     clocks = sampler.stop()
@@ -927,11 +975,11 @@ def run_ours(args):
             line["full_run"], full_pairs = r
         else:
             line["full_run"] = r
-    if args.strong_gib > 0:
+    if args.strong_gib > 0 or args.strong_mib > 0:
         line["strong_cfg4"] = guarded("strong_cfg4", strong_leg, args, eng, 0, 1, local)
     if args.encode_gb > 0:
         def enc():
-            m = full_pairs if full_pairs is not None else merges_for_encode(eng, 32512)
+            m = full_pairs if full_pairs is not None else merges_for_encode(eng, args.encode_merges, args.encode_train_mib)
             return encode_leg(args, eng, 0, 1, m)
         line["encode_cfg5"] = guarded("encode_cfg5", enc)
     dog.disarm()
@@ -1015,12 +1063,15 @@ def main():
     ap.add_argument("--strong-gib", type=int, default=16,
                     help="also run BASELINE configs[3] (strong scaling: this many GiB in total over the N GPUs, vocab "
                          "--strong-vocab) and report it as strong_cfg4; 0 = skip")
+    ap.add_argument("--strong-mib", type=int, default=0, help="size of the strong leg in MiB instead of --strong-gib (small runs, tests)")
     ap.add_argument("--strong-vocab", type=int, default=100000)
     ap.add_argument("--strong-sparse-at", type=int, default=1000, help="first merge of the second (sparse) timed window of the strong leg")
     ap.add_argument("--strong-check", type=int, default=256, help="merges of the strong leg compared with the oracle (0 = none)")
     ap.add_argument("--encode-gb", type=float, default=4.0,
                     help="also run BASELINE configs[4] (encode this many 1e9 bytes with a 32k merges table; N GPUs = replicas over "
                          "byte-range shards) and report it as encode_cfg5; 0 = skip")
+    ap.add_argument("--encode-merges", type=int, default=32512, help="merges of the table the encode leg uses when the run has not trained one")
+    ap.add_argument("--encode-train-mib", type=int, default=256, help="... trained on this many MiB of the cfg3 corpus")
     ap.add_argument("--exchange", default=os.environ.get("BPE_EXCHANGE", "collective"), choices=["collective", "p2p"],
                     help="N>1: per-merge exchange of the sharded loop. collective = two NCCL all-reduces (validated on 2/4/8 B200s); "
                          "p2p = the hand-written NVLink peer-memory kernels of k_xchg.cuh (opt-in until validated on hardware)")

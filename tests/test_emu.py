@@ -9,7 +9,12 @@ It is a logic check for a container without a GPU, NOT a product path (nothing i
 build) and not a substitute for `-m gpu` on a B200: performance, the PTX paths (TMA / mbarrier are emulated as
 immediate copies) and the cross-GPU memory model are out of its reach.
 
-The four jobs start together (they are independent processes) and each test waits for its own job."""
+bench.py itself is executed the same way (BPE_BENCH_EMU=1: gloo instead of NCCL, host tensors, tiny sizes), N = 1 and
+N = 2 ranks under torchrun, every leg: contract line, whole-loop run, cfg4 strong leg, cfg5 encode leg — so that the
+control flow the driver will run at round end has been executed at least once, with its parity checks green.
+
+The jobs start together (they are independent processes) and each test waits for its own job."""
+import json
 import os
 import subprocess
 import sys
@@ -52,6 +57,14 @@ def jobs():
         "sharded": subprocess.Popen([sys.executable, os.path.join(EMU, "emu_sharded.py"), "2:collective", "2:p2p", "3:p2p", "4:p2p"],
                                     cwd=ROOT, env=_env(lib), stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True),
     }
+    bench_args = ["--size-mib", "1", "--steps", "6", "--warmup", "3", "--strong-mib", "2", "--strong-sparse-at", "24", "--strong-check", "16",
+                  "--encode-gb", "0.002", "--encode-merges", "200", "--encode-train-mib", "1", "--leg-budget-s", "600"]
+    benv = dict(_env(lib), BPE_BENCH_EMU="1")
+    procs["bench1"] = subprocess.Popen([sys.executable, "bench.py", "--full-merges", "40"] + bench_args, cwd=ROOT, env=benv,
+                                       stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True)
+    procs["bench2"] = subprocess.Popen([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2",
+                                        "--master-addr", "127.0.0.1", "--master-port", "29547", "bench.py", "--gpus", "2"] + bench_args,
+                                       cwd=ROOT, env=benv, stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True)
     yield procs
     for p in procs.values():
         if p.poll() is None:
@@ -89,6 +102,48 @@ def test_emu_sharded_loop_collective_and_p2p(jobs):
     out = _finish(jobs, "sharded")
     assert "emu sharded ok" in out
     assert out.count("bit-exact on every rank") == 12
+
+
+def _bench_line(jobs, name):
+    p = jobs[name]
+    try:
+        out, err = p.communicate(timeout=1500)
+    except subprocess.TimeoutExpired:
+        p.kill()
+        out, err = p.communicate()
+        pytest.fail(f"{name} did not finish\n{err[-3000:]}")
+    assert p.returncode == 0, err[-6000:]
+    lines = [ln for ln in out.splitlines() if ln.startswith("{")]
+    assert len(lines) == 1, out[-2000:]          # the contract: ONE JSON line
+    return json.loads(lines[0])
+
+
+CONTRACT_KEYS = ("metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_step", "higher_is_better", "scaling", "vs_baseline",
+                 "dtype", "data", "config", "clocks", "e2e", "gpu_launches", "roofline", "cpu_baseline")
+
+
+def test_emu_bench_one_rank_every_leg(jobs):
+    d = _bench_line(jobs, "bench1")
+    for k in CONTRACT_KEYS:
+        assert k in d, k
+    assert d["n_gpus"] == 1 and d["steps"] == 6 and d["gpu_launches"] > 0 and "workload" in d["config"]
+    assert d["e2e"]["h2d_bytes_per_step"] > 0 and d["cpu_baseline"]["kind"] == "port"
+    assert d["full_run"]["parity_all_merges"] is True and d["full_run"]["merges"] == 40
+    assert d["strong_cfg4"]["parity_vs_oracle"]["equal"] is True
+    assert d["encode_cfg5"]["parity"]["equal"] is True and d["encode_cfg5"]["memo"]["fallback_pieces"] == 0
+    test_emu_bench_one_rank_every_leg.sha = d["strong_cfg4"]["merges_sha16"]
+
+
+def test_emu_bench_two_ranks_every_leg(jobs):
+    d = _bench_line(jobs, "bench2")
+    for k in CONTRACT_KEYS:
+        assert k in d, k
+    assert d["n_gpus"] == 2 and d["config"]["consistent"] is True and d["config"]["exchange_used"] == "collective"
+    assert d["strong_cfg4"]["parity_vs_oracle"]["equal"] is True
+    assert d["encode_cfg5"]["parity"]["equal"] is True
+    sha1 = getattr(test_emu_bench_one_rank_every_leg, "sha", None)
+    if sha1 is not None:      # strong scaling: the same corpus on 1 and on 2 ranks gives the same merges
+        assert d["strong_cfg4"]["merges_sha16"] == sha1
 
 
 def test_emulator_is_not_a_product_path():
