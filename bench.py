@@ -1075,7 +1075,7 @@ def main():
     ap.add_argument("--exchange", default=os.environ.get("BPE_EXCHANGE", "collective"), choices=["collective", "p2p"],
                     help="N>1: per-merge exchange of the sharded loop. collective = two NCCL all-reduces (validated on 2/4/8 B200s); "
                          "p2p = the hand-written NVLink peer-memory kernels of k_xchg.cuh (opt-in until validated on hardware)")
-    ap.add_argument("--leg-budget-s", type=int, default=900,
+    ap.add_argument("--leg-budget-s", type=int, default=600,
                     help="wall-clock budget of the optional legs (whole-loop run, cfg4, cfg5) after the contract line is complete; "
                          "when it runs out the line is printed with the legs finished so far")
     ap.add_argument("--extras", action="store_true", help="side measurements (cfg2 wall time, encode throughput)")

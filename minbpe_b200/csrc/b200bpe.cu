@@ -62,7 +62,7 @@ struct bpe_handle {
     bool xchg_attached = false;
     u32 *d_present = nullptr;   // sharded loop: bitmap of pair hashes that have occurred in this shard (k_stats.cuh)
     unsigned char *split_slab = nullptr; u64 split_cap = 0;   // working set of the splitter, kept between calls (split_host.inl)
-    int argmax_grid = 0, merge_grid = 0, merge_grid_same = 0, merge_grid_seg = 0, ff_grid = 0;
+    int argmax_grid = 0, merge_grid_same = 0, merge_grid_seg = 0, ff_grid = 0;
 
     // options
     int step_poll_every = 16;
@@ -159,12 +159,9 @@ extern "C" int bpe_create(int device, bpe_handle **out) {
     if ((e = cudaMallocHost(&h->h_ctl, sizeof(Ctl))) != cudaSuccess) return bail("cudaMallocHost", e);
     if ((e = cudaMalloc(&h->dense, 65536 * 8)) != cudaSuccess) return bail("cudaMalloc dense", e);
     if ((e = cudaMalloc(&h->d_err, 8)) != cudaSuccess) return bail("cudaMalloc err", e);   // [0] error flag, [1] max id seen by k_copy_ids
-    int occ = 1;
     int occ_same = 1;
     cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_same, k_merge<true>, MG_THREADS, 0);
-    if (occ < 1) occ = 1;
     if (occ_same < 1) occ_same = 1;
-    h->merge_grid = h->sms * occ;
     h->merge_grid_same = h->sms * occ_same;
     int occ_fast = 0;
     if ((e = cudaFuncSetAttribute(k_merge_seg, cudaFuncAttributeMaxDynamicSharedMemorySize, MS_SMEM_BYTES)) != cudaSuccess)
@@ -580,7 +577,6 @@ static int build_table(bpe_handle *h, u64 cap) {
     }
     const ull zero = 0;
     CU(cudaMemcpyAsync(&h->ctl->table_used, &zero, 8, cudaMemcpyHostToDevice, h->stream));
-    const u64 n = h->h_ctl->n;
     if (h->bytes_only) {
         CU(cudaMemsetAsync(h->dense, 0, 65536 * 8, h->stream));
         CU(cudaMemsetAsync(h->d_err, 0, 4, h->stream));

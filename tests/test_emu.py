@@ -46,8 +46,8 @@ def jobs():
     lib = build_emu.build()
     t = lambda f: os.path.join("tests", f)  # noqa: E731
     procs = {
-        # the round-2 kernels that have not run on a GPU yet: memoised chunk encode (k_encode2.cuh), bpe_replay / resume,
-        # bpe_decode
+        # round-2 kernels that have not run on a GPU yet — memoised chunk encode (k_encode2.cuh), bpe_replay / resume —
+        # and bpe_decode
         "new_kernels": _pytest(lib, [t("test_gpu_zy_encode2.py"), t("test_gpu_zz_resume.py"), t("test_gpu_decode.py")]),
         # kernels already validated on B200s, as a check of the emulator itself (golden vectors of the reference)
         "validated_kernels": _pytest(lib, [t("test_gpu_parity.py")],
@@ -57,6 +57,8 @@ def jobs():
         "sharded": subprocess.Popen([sys.executable, os.path.join(EMU, "emu_sharded.py"), "2:collective", "2:p2p", "3:p2p", "4:p2p"],
                                     cwd=ROOT, env=_env(lib), stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True),
     }
+    procs["fuzz"] = subprocess.Popen([sys.executable, os.path.join(EMU, "emu_fuzz_encode.py"), "120", "7"], cwd=ROOT, env=_env(lib),
+                                     stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
     bench_args = ["--size-mib", "1", "--steps", "6", "--warmup", "3", "--strong-mib", "2", "--strong-sparse-at", "24", "--strong-check", "16",
                   "--encode-gb", "0.002", "--encode-merges", "200", "--encode-train-mib", "1", "--leg-budget-s", "600"]
     benv = dict(_env(lib), BPE_BENCH_EMU="1")
@@ -102,6 +104,10 @@ def test_emu_sharded_loop_collective_and_p2p(jobs):
     out = _finish(jobs, "sharded")
     assert "emu sharded ok" in out
     assert out.count("bit-exact on every rank") == 12
+
+
+def test_emu_encode_fuzz_under_guard_pages(jobs):
+    assert "emu fuzz encode ok" in _finish(jobs, "fuzz")
 
 
 def _bench_line(jobs, name):
