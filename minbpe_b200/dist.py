@@ -272,11 +272,13 @@ def train_file(engine, device, path, num_merges, first_idx=256, group=None, poll
     return tr.result()
 
 
-def encode_sharded(engine, data, offsets, merges, byte_perm=None, group=None, gather=False):
+def encode_sharded(engine, data, offsets, merges, byte_perm=None, group=None, gather=False, rank=None, world=None):
     """regex.py:111-121 over `world` GPUs: chunks are independent, so encode needs no exchange at all —
     every rank encodes its contiguous chunk range (replicas over byte-range shards).  Returns this
-    rank's ids; with gather=True rank 0 also gets the concatenation in text order (others: None)."""
-    rank, world = dist.get_rank(group), dist.get_world_size(group)
+    rank's ids; with gather=True rank 0 also gets the concatenation in text order (others: None).
+    rank / world default to the process group's."""
+    rank = dist.get_rank(group) if rank is None else rank
+    world = dist.get_world_size(group) if world is None else world
     raw = np.frombuffer(data, dtype=np.uint8) if not isinstance(data, np.ndarray) else data
     blo, bhi, clo, chi = shard_chunks(raw.size, offsets, rank, world)
     local_offs = np.asarray(offsets[clo:chi], dtype=np.uint64) - np.uint64(blo)
