@@ -22,14 +22,17 @@
 #include "k_decode.cuh"
 #include "k_xchg.cuh"
 #include "k_encode2.cuh"
+#include "k_special.cuh"
 
 #define BPE_ABI_VERSION 1
 
 struct EncState;
+struct SpecSet;
 struct bpe_handle {
     int device = 0;
     EncState *enc = nullptr;          // memoised chunk encode (encode2_host.inl): rank table, memo, id pool, scratch
     bpe_handle *enc_scratch = nullptr;   // general encode path (encode_host.inl) works on its own stream buffers
+    SpecSet *spec = nullptr;             // special tokens of the current encode call (special_host.inl)
     int sms = 0;
     cudaStream_t stream = nullptr;       // the stream every kernel of this handle runs on
     cudaStream_t own_stream = nullptr;   // created by bpe_create; `stream` may point at a caller's stream instead
@@ -78,6 +81,7 @@ struct bpe_handle {
 static thread_local std::string g_create_err;
 static void xchg_release(bpe_handle *h);
 static void enc2_free(bpe_handle *h);
+static void spec_free(bpe_handle *h);
 static u64 g_split_piece_override = 0;   // BPE_OPT_SPLIT_PIECE (test hook): bytes per piece of the device splitter
 
 static int fail(bpe_handle *h, int code, const std::string &msg) {
@@ -201,6 +205,7 @@ extern "C" int bpe_destroy(bpe_handle *h) {
     if (h->d_present) cudaFree(h->d_present);
     xchg_release(h);
     enc2_free(h);
+    spec_free(h);
     if (h->enc_scratch) bpe_destroy(h->enc_scratch);
     if (h->split_slab) cudaFree(h->split_slab);
     if (h->ctl) cudaFree(h->ctl);
@@ -785,6 +790,7 @@ extern "C" int bpe_debug_table(bpe_handle *h, int32_t *pairs, int64_t *counts, u
 
 #include "encode_host.inl"
 #include "step_host.inl"
+#include "special_host.inl"
 #include "split_host.inl"
 #include "encode2_host.inl"
 #include "decode_host.inl"

@@ -5,6 +5,7 @@
 struct EncState {
     // rank table of the merges the memo was built for
     u64 merges_hash = 0; int n_merges = -1; bool has_perm = false; u64 perm_hash = 0;
+    u64 spec_hash = 0;                // special tokens seeded into the memo (0 = none)
     int *d_merges = nullptr; u64 *d_rkeys = nullptr; u32 *d_rranks = nullptr; u64 rt_cap = 0;
     unsigned char *d_perm = nullptr;
     MemoSlot *memo = nullptr; u64 memo_cap = 0;
@@ -43,15 +44,33 @@ static void enc2_free(bpe_handle *h) {
 
 #define E2CU(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) return fail(h, BPE_ERR_CUDA, std::string(#call) + ": " + cudaGetErrorString(e_)); } while (0)
 
+static Enc2 enc2_args(const EncState *S) {
+    Enc2 E;
+    E.text = nullptr; E.flag = nullptr; E.n = 0;
+    E.memo = S->memo; E.memo_mask = S->memo_cap - 1; E.memo_limit = S->memo_cap / 2;
+    E.pool = S->pool; E.pool_cap = S->pool_cap;
+    E.new_list = S->new_list; E.new_cap = (u32)S->memo_cap;
+    E.direct_list = S->direct_list; E.direct_cap = S->direct_cap;
+    E.posmap = nullptr; E.pos_mask = 0;
+    E.ctl = S->ctl;
+    return E;
+}
+
+// empty table; the special tokens of the current call (if any) are entries from the start
 static int enc2_reset_memo(bpe_handle *h) {
     EncState *S = h->enc;
     E2CU(cudaMemsetAsync(S->memo, 0, S->memo_cap * sizeof(MemoSlot), h->stream));
     E2CU(cudaMemsetAsync(S->ctl, 0, sizeof(EncCtl), h->stream));
+    const SpecSet *P = h->spec;
+    if (S->spec_hash && P && P->k) {
+        k_enc_seed_specials<<<1, SPEC_MAX, 0, h->stream>>>(enc2_args(S), P->d_blob, P->d_off, P->d_ids, P->k);
+        h->tm.kernel_launches += 1;
+    }
     return BPE_OK;
 }
 
 // rank table + memo for this merges table (kept while the caller keeps passing the same merges)
-static int enc2_prepare(bpe_handle *h, const int32_t *merges, int32_t n_merges, const uint8_t *perm) {
+static int enc2_prepare(bpe_handle *h, const int32_t *merges, int32_t n_merges, const uint8_t *perm, bool use_spec = false) {
     if (!h->enc) h->enc = new (std::nothrow) EncState();
     EncState *S = h->enc;
     if (!S) return fail(h, BPE_ERR_INTERNAL, "out of host memory");
@@ -67,7 +86,10 @@ static int enc2_prepare(bpe_handle *h, const int32_t *merges, int32_t n_merges, 
         S->n_merges = -1;
     }
     const u64 mh = fnv64(merges, (size_t)n_merges * 8), ph = perm ? fnv64(perm, 256) : 0;
-    if (S->n_merges == n_merges && S->merges_hash == mh && S->has_perm == (perm != nullptr) && S->perm_hash == ph) return BPE_OK;
+    const u64 sh = (use_spec && h->spec && h->spec->k) ? h->spec->hash : 0;
+    if (S->n_merges == n_merges && S->merges_hash == mh && S->has_perm == (perm != nullptr) && S->perm_hash == ph && S->spec_hash == sh)
+        return BPE_OK;
+    S->spec_hash = sh;
     const u64 tcap = next_pow2(std::max<u64>(1024, 4ull * (u64)n_merges));
     if (tcap > S->rt_cap) {
         cudaFree(S->d_rkeys); cudaFree(S->d_rranks); cudaFree(S->d_merges);
@@ -118,14 +140,8 @@ static int enc2_piece(bpe_handle *h, const unsigned char *d_text, const unsigned
     hc.n_new = 0; hc.n_direct = 0; hc.n_long = 0; hc.fail = 0;
     E2CU(cudaMemcpyAsync(S->ctl, &hc, sizeof(EncCtl), cudaMemcpyHostToDevice, h->stream));
 
-    Enc2 E;
+    Enc2 E = enc2_args(S);
     E.text = d_text; E.flag = d_flag; E.n = m;
-    E.memo = S->memo; E.memo_mask = S->memo_cap - 1; E.memo_limit = S->memo_cap / 2;
-    E.pool = S->pool; E.pool_cap = S->pool_cap;
-    E.new_list = S->new_list; E.new_cap = (u32)S->memo_cap;
-    E.direct_list = S->direct_list; E.direct_cap = S->direct_cap;
-    E.posmap = nullptr; E.pos_mask = 0;
-    E.ctl = S->ctl;
     const RankTable rt = {S->d_rkeys, S->d_rranks, S->rt_cap - 1};
     const unsigned char *perm = S->has_perm ? S->d_perm : nullptr;
     cudaEvent_t e0 = nullptr, e1 = nullptr;
@@ -230,33 +246,100 @@ static int enc2_piece_fallback(bpe_handle *h, const uint8_t *host_bytes, const u
     return rc;
 }
 
-// regex.py:111-121 without the host in the middle: upload the text, split it with the GPT-4 pattern on the device,
-// encode every chunk, return the ids.  No offsets array exists anywhere.
-extern "C" int bpe_encode_text_gpt4(bpe_handle *h, const uint8_t *bytes, uint64_t n, const int32_t *merges, int32_t n_merges,
-                                    const uint8_t *byte_perm, int32_t *out_ids, uint64_t out_cap, uint64_t *out_n) {
-    if (!h || !out_n || (!bytes && n) || n_merges < 0 || (n_merges && !merges)) return BPE_ERR_ARG;
-    CU(cudaSetDevice(h->device));
+// general path for one piece that contains special tokens: every part between two occurrences is encoded on its own
+// (regex.py:159-163), the occurrences contribute their ids
+static int enc2_piece_fallback_special(bpe_handle *h, const uint8_t *host_bytes, const unsigned char *d_flag, u64 m,
+                                       const std::vector<u64> &hits, const std::vector<unsigned char> &which, const int32_t *merges,
+                                       int32_t n_merges, const uint8_t *perm, int32_t *out, u64 cap, u64 *written) {
+    u64 *d_offs = nullptr;
+    E2CU(cudaMalloc(&d_offs, m * 8));
+    u64 k = 0;
+    int rc = flags_to_offsets(h, d_flag, m, d_offs, &k, 0);
+    std::vector<u64> offs;
+    if (!rc) {
+        offs.resize(k);
+        cudaError_t e = cudaMemcpyAsync(offs.data(), d_offs, k * 8, cudaMemcpyDeviceToHost, h->stream);
+        if (e == cudaSuccess) e = cudaStreamSynchronize(h->stream);
+        if (e != cudaSuccess) rc = fail(h, BPE_ERR_CUDA, cudaGetErrorString(e));
+    }
+    cudaFree(d_offs);
+    if (rc) return rc;
+    u64 lo = 0;
+    std::vector<u64> rel;
+    for (size_t j = 0; j <= hits.size(); ++j) {
+        const u64 hi = j < hits.size() ? (hits[j] >> 8) : m;
+        if (hi > lo) {      // ordinary part [lo, hi): its chunk starts are the flags inside it
+            const u64 *f0 = std::lower_bound(offs.data(), offs.data() + k, lo), *f1 = std::lower_bound(offs.data(), offs.data() + k, hi);
+            rel.assign(f0, f1);
+            for (u64 &x : rel) x -= lo;
+            u64 got = 0;
+            if ((rc = encode_general(h, host_bytes + lo, hi - lo, rel.data(), rel.size(), merges, n_merges, perm, out + *written, cap - *written, &got))) return rc;
+            *written += got;
+        }
+        if (j < hits.size()) {
+            if (*written >= cap) return fail(h, BPE_ERR_CAPACITY, "output buffer too small");
+            out[(*written)++] = h->spec->ids[which[j]];
+            lo = hi + (hits[j] & 0xffu);
+        }
+    }
+    return BPE_OK;
+}
+
+// regex.py:111-121 (and, with special tokens, regex.py:152-163) without the host in the middle: upload the text, find
+// the special tokens, split with the GPT-4 pattern, encode every chunk, return the ids.  No offsets array anywhere.
+static int encode_text_impl(bpe_handle *h, const uint8_t *bytes, uint64_t n, const int32_t *merges, int32_t n_merges,
+                            const uint8_t *byte_perm, bool use_spec, int32_t *out_ids, uint64_t out_cap, uint64_t *out_n) {
     *out_n = 0;
     h->tm.h2d_bytes = 0; h->tm.d2h_bytes = 0; h->tm.kernel_launches = 0; h->tm.init_ms = 0;
     if (n == 0) return BPE_OK;
-    int rc = enc2_prepare(h, merges, n_merges, byte_perm);
+    use_spec = use_spec && h->spec && h->spec->k;
+    int rc = enc2_prepare(h, merges, n_merges, byte_perm, use_spec);
     if (rc) return rc;
     EncState *S = h->enc;
     S->st_chunks_new = S->st_direct = S->st_long = S->st_pieces = S->st_fallbacks = 0; S->st_kernel_ms = 0;
     const u64 piece = g_split_piece_override ? g_split_piece_override : SPLIT_PIECE_BYTES;
     u64 written = 0;
+    std::vector<u64> hits;
+    std::vector<unsigned char> which;
     for (u64 s = 0; s < n;) {
-        const u64 e = split_piece_end(bytes, n, s, piece);
+        const u64 e = split_piece_end(bytes, n, s, piece, use_spec ? h->spec : nullptr);
         if (!e) return fail(h, BPE_ERR_ARG, "no letter+space cut point within a piece of the text (cannot split it piecewise)");
         SplitWork W;
-        if ((rc = split_run(h, bytes + s, e - s, W, nullptr))) return rc;
+        if ((rc = split_run(h, bytes + s, e - s, W, nullptr, use_spec ? &hits : nullptr, use_spec ? &which : nullptr))) return rc;
         int fb = 0;
         if ((rc = enc2_piece(h, W.bytes, W.flag, e - s, out_ids, out_cap, &written, &fb))) return rc;
-        if (fb && (rc = enc2_piece_fallback(h, bytes + s, W.flag, e - s, merges, n_merges, byte_perm, out_ids, out_cap, &written))) return rc;
+        if (fb) {
+            if (use_spec && !hits.empty())
+                rc = enc2_piece_fallback_special(h, bytes + s, W.flag, e - s, hits, which, merges, n_merges, byte_perm, out_ids, out_cap, &written);
+            else
+                rc = enc2_piece_fallback(h, bytes + s, W.flag, e - s, merges, n_merges, byte_perm, out_ids, out_cap, &written);
+            if (rc) return rc;
+        }
         s = e;
     }
     *out_n = written;
     return BPE_OK;
+}
+
+extern "C" int bpe_encode_text_gpt4(bpe_handle *h, const uint8_t *bytes, uint64_t n, const int32_t *merges, int32_t n_merges,
+                                    const uint8_t *byte_perm, int32_t *out_ids, uint64_t out_cap, uint64_t *out_n) {
+    if (!h || !out_n || (!bytes && n) || n_merges < 0 || (n_merges && !merges)) return BPE_ERR_ARG;
+    CU(cudaSetDevice(h->device));
+    return encode_text_impl(h, bytes, n, merges, n_merges, byte_perm, false, out_ids, out_cap, out_n);
+}
+
+// RegexTokenizer.encode(text, allowed_special=...) (regex.py:123-164) in one call: the special tokens (their utf-8 bytes
+// back to back, k + 1 offsets, k ids; in the order of the special_tokens dict, which is the order the reference's regex
+// tries them in) are found on the device and every part between them is split and encoded on its own.
+extern "C" int bpe_encode_text_gpt4_special(bpe_handle *h, const uint8_t *bytes, uint64_t n, const int32_t *merges, int32_t n_merges,
+                                            const uint8_t *byte_perm, const uint8_t *special_bytes, const uint32_t *special_offsets,
+                                            const int32_t *special_ids, int32_t n_special, int32_t *out_ids, uint64_t out_cap,
+                                            uint64_t *out_n) {
+    if (!h || !out_n || (!bytes && n) || n_merges < 0 || (n_merges && !merges)) return BPE_ERR_ARG;
+    CU(cudaSetDevice(h->device));
+    int rc = spec_set(h, special_bytes, special_offsets, special_ids, n_special);
+    if (rc) return rc;
+    return encode_text_impl(h, bytes, n, merges, n_merges, byte_perm, true, out_ids, out_cap, out_n);
 }
 
 // bpe_encode with the caller's chunk offsets (any split pattern): text + offsets up, flags from the offsets

@@ -121,12 +121,22 @@ __device__ __forceinline__ u32 e2_chunk_len(const E2Tile &T, u32 p) {
     return len > E2_LMAX ? E2_LMAX + 1 : len;
 }
 
+// 64-bit tag of a chunk from its zero-padded key words (never 0: bit 0 is set)
+__device__ __forceinline__ u64 e2_tag(const u32 (&kw)[8], u32 len) {
+    u64 h = 0x9e3779b97f4a7c15ull ^ ((u64)len << 56);
+    h = hash64(h ^ ((u64)kw[0] | ((u64)kw[1] << 32)));
+    if (len > 8) {
+        h = hash64(h ^ ((u64)kw[2] | ((u64)kw[3] << 32)));
+        if (len > 16) { h = hash64(h ^ ((u64)kw[4] | ((u64)kw[5] << 32))); h = hash64(h ^ ((u64)kw[6] | ((u64)kw[7] << 32))); }
+    }
+    return h | 1ull;
+}
+
 // key words of the chunk [p, p+len) of the tile (len <= E2_LMAX): zero padded; returns the tag
 __device__ __forceinline__ u64 e2_key(const E2Tile &T, u32 p, u32 len, u32 (&kw)[8]) {
     const u32 *s32 = reinterpret_cast<const u32 *>(T.s_b);
     const u32 w0 = p >> 2, sh = (p & 3u) * 8u;
     const u32 nw = (len + 3u) >> 2;
-    u64 h = 0x9e3779b97f4a7c15ull ^ ((u64)len << 56);
 #pragma unroll
     for (u32 j = 0; j < 8; ++j) {
         u32 v = 0;
@@ -137,12 +147,7 @@ __device__ __forceinline__ u64 e2_key(const E2Tile &T, u32 p, u32 len, u32 (&kw)
         }
         kw[j] = v;
     }
-    h = hash64(h ^ ((u64)kw[0] | ((u64)kw[1] << 32)));
-    if (len > 8) {
-        h = hash64(h ^ ((u64)kw[2] | ((u64)kw[3] << 32)));
-        if (len > 16) { h = hash64(h ^ ((u64)kw[4] | ((u64)kw[5] << 32))); h = hash64(h ^ ((u64)kw[6] | ((u64)kw[7] << 32))); }
-    }
-    return h | 1ull;
+    return e2_tag(kw, len);
 }
 
 __device__ __forceinline__ void e2_direct_append(const Enc2 &E, u64 pos, bool is_long) {
@@ -196,6 +201,41 @@ __global__ void __launch_bounds__(E2_THREADS) k_enc_insert(Enc2 E) {
         }
         if (!placed) e2_direct_append(E, lo + p, false);
     }
+}
+
+// Special tokens (regex.py:152-163) as memo entries: the occurrence of a special is one chunk (k_special.cuh) whose
+// "encoding" is its single id.  One thread per special, on a freshly cleared table.
+__global__ void k_enc_seed_specials(Enc2 E, const unsigned char *__restrict__ blob, const u32 *__restrict__ off,
+                                    const int *__restrict__ ids, int k) {
+    const int s = blockIdx.x * blockDim.x + threadIdx.x;
+    if (s >= k) return;
+    const u32 lo = off[s], len = off[s + 1] - lo;      // 1 .. E2_LMAX (checked by the host)
+    u32 kw[8];
+#pragma unroll
+    for (u32 j = 0; j < 8; ++j) {
+        u32 v = 0;
+        for (u32 t = 0; t < 4; ++t) if (4 * j + t < len) v |= (u32)blob[lo + 4 * j + t] << (8 * t);
+        kw[j] = v;
+    }
+    const u64 tag = e2_tag(kw, len);
+    u64 slot = (tag >> 1) & E.memo_mask;
+    for (u64 probe = 0; probe <= E.memo_mask; ++probe) {
+        const u64 old = atomicCAS((ull *)&E.memo[slot].tag, 0ull, (ull)tag);
+        if (old == 0) {
+            MemoSlot *m = &E.memo[slot];
+            const ull o = atomicAdd(&E.ctl->pool_used, 1ull);
+            if (o >= E.pool_cap) { E.ctl->fail = 1; return; }
+            E.pool[o] = (u32)ids[s];
+            m->off = (u32)o;
+#pragma unroll
+            for (int j = 0; j < 8; ++j) m->key[j] = kw[j];
+            m->meta = len | (1u << 8);
+            atomicAdd(&E.ctl->memo_used, 1ull);
+            return;
+        }
+        slot = (slot + 1) & E.memo_mask;
+    }
+    E.ctl->fail = 1;
 }
 
 // regex.py:92-109 on a short token list held by one thread.  tok[] in/out, returns the new length.

@@ -61,7 +61,8 @@ __device__ __forceinline__ T block_reduce_ordered(T v, OP op, T *sm, u32 nthread
     return r;
 }
 
-// tile aggregates of both scans
+// tile aggregates of both scans (WITH_B: the class array may hold special-token boundaries, k_special.cuh)
+template <bool WITH_B>
 __global__ void __launch_bounds__(SP_THREADS) k_split_reduce(const unsigned char *__restrict__ meta, u64 n,
                                                              SplFwd *__restrict__ fpart, SplBwd *__restrict__ bpart) {
     __shared__ SplFwd sf[SP_THREADS];
@@ -80,7 +81,7 @@ __global__ void __launch_bounds__(SP_THREADS) k_split_reduce(const unsigned char
         if (base + k < n) f = spl_fwd_combine(f, spl_fwd_elem(base + k, m[k + 1], m[k]));
 #pragma unroll
     for (int k = SP_ITEMS - 1; k >= 0; --k)
-        if (base + k < n) g = spl_bwd_combine(spl_bwd_elem(base + k, n, m[k + 1], m[k + 2]), g);
+        if (base + k < n) g = spl_bwd_combine(spl_bwd_elem<WITH_B>(base + k, n, m[k + 1], m[k + 2]), g);
     f = block_reduce_ordered(f, FwdOp(), sf, SP_THREADS);
     g = block_reduce_ordered(g, BwdOp(), sb, SP_THREADS);
     if (threadIdx.x == 0) { fpart[blockIdx.x] = f; bpart[blockIdx.x] = g; }
@@ -116,7 +117,7 @@ __global__ void __launch_bounds__(1024) k_split_scan_parts(SplFwd *__restrict__ 
 }
 
 // per tile: scans + rule.  TOKENS = false: flag[i] = 1 at chunk starts.  TOKENS = true: dst[i] = byte | chunk mark.
-template <bool TOKENS>
+template <bool TOKENS, bool WITH_B>
 __global__ void __launch_bounds__(SP_THREADS) k_split_apply(const unsigned char *__restrict__ b, const unsigned char *__restrict__ meta, u64 n,
                                                             const unsigned char *__restrict__ contr,
                                                             const SplFwd *__restrict__ fpart, const SplBwd *__restrict__ bpart,
@@ -143,7 +144,7 @@ __global__ void __launch_bounds__(SP_THREADS) k_split_apply(const unsigned char 
     SplBwd g = spl_bwd_identity();
 #pragma unroll
     for (int k = 0; k < SP_ITEMS; ++k) {
-        if (base + k < n) { fe[k] = spl_fwd_elem(base + k, mm[k], mm[k - 1]); ge[k] = spl_bwd_elem(base + k, n, mm[k], mm[k + 1]); }
+        if (base + k < n) { fe[k] = spl_fwd_elem(base + k, mm[k], mm[k - 1]); ge[k] = spl_bwd_elem<WITH_B>(base + k, n, mm[k], mm[k + 1]); }
         else { fe[k] = spl_fwd_identity(); ge[k] = spl_bwd_identity(); }
         f = spl_fwd_combine(f, fe[k]);
     }
@@ -173,7 +174,7 @@ __global__ void __launch_bounds__(SP_THREADS) k_split_apply(const unsigned char 
         const SplFwd fprev = frun;
         frun = spl_fwd_combine(frun, fe[k]);
         bool st = false;
-        if (i < n && (mm[k] & SM_START)) st = spl_chunk_start(i, n, frun, fprev, gi[k], B, M, contr);
+        if (i < n && (mm[k] & SM_START)) st = spl_chunk_start<WITH_B>(i, n, frun, fprev, gi[k], B, M, contr);
         out[k] = TOKENS ? ((u32)s_b[SP_HALO + tid * SP_ITEMS + k] | (st ? TOK_FLAG : 0u)) : (st ? 1u : 0u);
     }
     if (TOKENS) {

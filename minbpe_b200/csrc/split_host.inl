@@ -47,8 +47,11 @@ static int split_carve(bpe_handle *h, u64 n, SplitWork &W) {
 }
 
 // host text (n bytes of UTF-8) -> W.bytes on the device; then either W.flag[i] = 1 at every chunk start
-// (tokens == nullptr) or tokens[i] = byte | chunk mark
-static int split_run(bpe_handle *h, const uint8_t *bytes, u64 n, SplitWork &W, u32 *tokens) {
+// (tokens == nullptr) or tokens[i] = byte | chunk mark.  With `hits` (flags only): the occurrences of the handle's
+// special tokens (special_host.inl) are found first and become text boundaries of the split — every occurrence one
+// chunk, the text on either side split on its own (regex.py:152-163); hits / which return them.
+static int split_run(bpe_handle *h, const uint8_t *bytes, u64 n, SplitWork &W, u32 *tokens,
+                     std::vector<u64> *hits = nullptr, std::vector<unsigned char> *which = nullptr) {
     if (!h->d_cls) return fail(h, BPE_ERR_STATE, "call bpe_gpt4_tables first");
     if (n == 0) return BPE_OK;
     if (n >= 0xfffffff0ull) return fail(h, BPE_ERR_ARG, "device split handles at most 4 GiB - 16 per call");
@@ -60,10 +63,28 @@ static int split_run(bpe_handle *h, const uint8_t *bytes, u64 n, SplitWork &W, u
     cudaEvent_t e0 = nullptr, e1 = nullptr;
     if (h->opt_kernel_timing) { cudaEventCreate(&e0); cudaEventCreate(&e1); cudaEventRecord(e0, h->stream); }
     k_split_classify<<<h->sms * 8, 256, 0, h->stream>>>(W.bytes, n, h->d_cls, W.meta);
-    k_split_reduce<<<ntiles, SP_THREADS, 0, h->stream>>>(W.meta, n, W.fpart, W.bpart);
-    k_split_scan_parts<<<1, 1024, 0, h->stream>>>(W.fpart, W.bpart, ntiles);
-    if (tokens) k_split_apply<true><<<ntiles, SP_THREADS, 0, h->stream>>>(W.bytes, W.meta, n, h->d_contr, W.fpart, W.bpart, nullptr, tokens);
-    else k_split_apply<false><<<ntiles, SP_THREADS, 0, h->stream>>>(W.bytes, W.meta, n, h->d_contr, W.fpart, W.bpart, W.flag, nullptr);
+    bool with_b = false;
+    if (hits && !tokens) {
+        if ((rc = spec_find(h, W.bytes, n, *hits, *which))) return rc;
+        if (!hits->empty()) {
+            if ((rc = spec_upload_hits(h, *hits))) return rc;
+            k_special_meta<<<grid_for(hits->size(), 256, h->sms * 8), 256, 0, h->stream>>>(W.meta, h->spec->d_hit, hits->size());
+            h->tm.kernel_launches += 1;
+            with_b = true;
+        }
+    }
+    if (with_b) {
+        k_split_reduce<true><<<ntiles, SP_THREADS, 0, h->stream>>>(W.meta, n, W.fpart, W.bpart);
+        k_split_scan_parts<<<1, 1024, 0, h->stream>>>(W.fpart, W.bpart, ntiles);
+        k_split_apply<false, true><<<ntiles, SP_THREADS, 0, h->stream>>>(W.bytes, W.meta, n, h->d_contr, W.fpart, W.bpart, W.flag, nullptr);
+        k_special_flags<<<grid_for(hits->size(), 256, h->sms * 8), 256, 0, h->stream>>>(W.flag, h->spec->d_hit, hits->size(), n);
+        h->tm.kernel_launches += 1;
+    } else {
+        k_split_reduce<false><<<ntiles, SP_THREADS, 0, h->stream>>>(W.meta, n, W.fpart, W.bpart);
+        k_split_scan_parts<<<1, 1024, 0, h->stream>>>(W.fpart, W.bpart, ntiles);
+        if (tokens) k_split_apply<true, false><<<ntiles, SP_THREADS, 0, h->stream>>>(W.bytes, W.meta, n, h->d_contr, W.fpart, W.bpart, nullptr, tokens);
+        else k_split_apply<false, false><<<ntiles, SP_THREADS, 0, h->stream>>>(W.bytes, W.meta, n, h->d_contr, W.fpart, W.bpart, W.flag, nullptr);
+    }
     h->tm.kernel_launches += 4;
     if (e0) {   // BPE_OPT_KERNEL_TIMING: device time of the four split kernels -> bpe_timing.init_ms
         cudaEventRecord(e1, h->stream); cudaEventSynchronize(e1);
@@ -106,13 +127,13 @@ static int flags_to_offsets(bpe_handle *h, const unsigned char *d_flag, u64 n, u
 
 // end of the piece that starts at s: n, or the last safe cut in (s + piece/2, s + piece] that is a multiple of 4
 // (the rule kernel stores the token words of a piece as 16-byte vectors: every piece must start 16-byte aligned
-// in the stream buffer); 0 = none found
-static u64 split_piece_end(const uint8_t *b, u64 n, u64 s, u64 piece) {
+// in the stream buffer); 0 = none found.  With special tokens a cut must not fall inside an occurrence of one.
+static u64 split_piece_end(const uint8_t *b, u64 n, u64 s, u64 piece, const SpecSet *spec = nullptr) {
     if (n - s <= piece) return n;
     const u64 hi = (s + piece) & ~3ull, lo = s + piece / 2;
     for (u64 p = hi; p > lo; p -= 4) {
         const uint8_t c = b[p - 1];
-        if (b[p] == 0x20 && ((c >= 'A' && c <= 'Z') || (c >= 'a' && c <= 'z'))) return p;
+        if (b[p] == 0x20 && ((c >= 'A' && c <= 'Z') || (c >= 'a' && c <= 'z')) && !spec_covers(spec, b, n, p)) return p;
     }
     return 0;
 }

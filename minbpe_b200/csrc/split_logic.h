@@ -22,6 +22,9 @@
 #define SC_SP 3u   // other \s
 #define SC_AP 4u   // apostrophe
 #define SC_O 5u    // everything else
+#define SC_B 6u    // bytes of a special-token occurrence (regex.py:152-163): the text on either side is split on its own, so such
+                   // a byte ends the runs around it and counts as "end of text" / "start of text" for its neighbours.  Only the
+                   // WITH_B instantiations of the functions below know this class; the plain GPT-4 split never produces it.
 #define SM_CLS 7u
 #define SM_START 8u     // meta bit: first byte of a UTF-8 sequence
 #define SPL_PK_NONE 7u  // "kind of the character in front of the run" at the start of the text
@@ -110,13 +113,15 @@ SPL_HD SplBwd spl_bwd_combine(SplBwd a, SplBwd b) {
     return r;
 }
 // element of byte i: mnext = meta of byte i+1 (ignored for i + 1 == n)
+template <bool WITH_B = false>
 SPL_HD SplBwd spl_bwd_elem(uint64_t i, uint64_t n, uint32_t m, uint32_t mnext) {
     const uint32_t cls = m & SM_CLS;
     const bool last = (i + 1 == n) || spl_kind(mnext & SM_CLS) != spl_kind(cls);
+    const bool text_ends = (i + 1 == n) || (WITH_B && (mnext & SM_CLS) == SC_B);
     SplBwd r;
     r.toend = (m & SM_START) ? 1u : 0u;
     r.bits = (cls == SC_NL ? SPL_B_NLAH : 0u);
-    if (last) r.bits |= SPL_B_LAST | (i + 1 == n ? SPL_B_ATEND : 0u);
+    if (last) r.bits |= SPL_B_LAST | (text_ends ? SPL_B_ATEND : 0u);
     return r;
 }
 
@@ -137,27 +142,36 @@ SPL_HD uint32_t spl_contraction_len(const Bytes &b, uint64_t n, const uint8_t *c
     return 0;
 }
 
+// byte x is a U+0020 of the text (with boundaries: not a 0x20 inside a special token)
+template <bool WITH_B, class Bytes, class Meta>
+SPL_HD bool spl_is_space20(const Bytes &b, const Meta &meta, uint64_t x) {
+    return b(x) == 0x20u && (!WITH_B || (meta(x) & SM_CLS) == SC_SP);
+}
+
 // the character [p, pend) is a one-character Oish run that itself starts a match (no U+0020 in front)
-template <class Bytes, class Meta>
+template <bool WITH_B = false, class Bytes, class Meta>
 SPL_HD bool spl_single_oish_start(const Bytes &b, const Meta &meta, uint64_t n, uint64_t p, uint64_t pend) {
     if (spl_kind(meta(p) & SM_CLS) != SC_O) return false;
     if (p > 0 && spl_kind(meta(p - 1) & SM_CLS) == SC_O) return false;
     if (pend < n && spl_kind(meta(pend) & SM_CLS) == SC_O) return false;
-    return p == 0 || b(p - 1) != 0x20u;
+    return p == 0 || !spl_is_space20<WITH_B>(b, meta, p - 1);
 }
 
 // ---- the rule -------------------------------------------------------------------------------
 // Does a chunk start at byte i?  i must be the first byte of a character.  f / g = inclusive forward /
 // backward scan values at byte i, fprev = forward value at byte i-1 (anything for i == 0).
 // Reads b() and meta() at most 12 bytes before and 8 bytes after i.
-template <class Bytes, class Meta>
+// WITH_B: bytes of class SC_B separate independently split texts (see SC_B); the caller overrides the answer for those
+// bytes themselves and for the byte that follows them.
+template <bool WITH_B = false, class Bytes, class Meta>
 SPL_HD bool spl_chunk_start(uint64_t i, uint64_t n, SplFwd f, SplFwd fprev, SplBwd g, const Bytes &b, const Meta &meta,
                             const uint8_t *contr) {
     if (i == 0) return true;
     const uint32_t cls = meta(i) & SM_CLS, kind = spl_kind(cls);
+    if (WITH_B && cls == SC_B) return false;
     const uint32_t before = f.since - 1u;            // characters of the run in front of this one
     if (kind == SC_N) return before % 3u == 0u;      // \p{N}{1,3}: groups of three from the start of the run
-    if (kind == SC_O) return before == 0u && b(i - 1) != 0x20u;   // with a space in front, the space starts the chunk
+    if (kind == SC_O) return before == 0u && !spl_is_space20<WITH_B>(b, meta, i - 1);   // with a space in front, the space starts the chunk
     if (kind == SC_SP) {
         const bool prev_oish = (f.bits & SPL_F_PK) == SC_O;       // " ?[^\s\p{L}\p{N}]++[\r\n]*" took the leading newlines
         const bool is_nl = cls == SC_NL;
@@ -176,12 +190,12 @@ SPL_HD bool spl_chunk_start(uint64_t i, uint64_t n, SplFwd f, SplFwd fprev, SplB
     if (before == 0u) {
         const uint64_t p = spl_char_start(b, i - 1);
         if ((meta(p) & SM_CLS) == SC_SP) return false;             // absorbed as the optional prefix
-        return !spl_single_oish_start(b, meta, n, p, i);
+        return !spl_single_oish_start<WITH_B>(b, meta, n, p, i);
     }
     if (before <= 2u) {   // second or third letter of a run that follows a contraction apostrophe: "'s|foo", "'ll|ama"
         uint64_t s = i;
         for (uint32_t c = 0; c < before; ++c) s = spl_char_start(b, s - 1);
-        if (s >= 1 && b(s - 1) == 0x27u && spl_single_oish_start(b, meta, n, s - 1, s)) {
+        if (s >= 1 && b(s - 1) == 0x27u && spl_single_oish_start<WITH_B>(b, meta, n, s - 1, s)) {
             const uint32_t clen = spl_contraction_len(b, n, contr, s);
             return clen != 0u && before == clen - 1u;
         }

@@ -58,6 +58,7 @@ def load_library():
         "bpe_replay": ([vp, vp, i32], ci),
         "bpe_encode": ([vp, vp, u64, vp, u64, vp, i32, vp, vp, u64, P(u64)], ci),
         "bpe_encode_text_gpt4": ([vp, vp, u64, vp, i32, vp, vp, u64, P(u64)], ci),
+        "bpe_encode_text_gpt4_special": ([vp, vp, u64, vp, i32, vp, vp, vp, vp, i32, vp, u64, P(u64)], ci),
         "bpe_encode_stats": ([vp, vp], ci),
         "bpe_get_timing": ([vp, P(Timing)], ci),
         "bpe_set_option": ([vp, ci, i64], ci),
@@ -219,8 +220,12 @@ class Engine:
             return out[: n.value].tobytes(), -1
         raise EngineError("bpe_decode: capacity retry failed")
 
-    def encode_text_gpt4(self, data, merges, byte_perm=None, out=None):
-        """-> ids int32 of utf-8 `data`: GPT-4 split + encode, both on the GPU (regex.py:111-121)."""
+    SPECIAL_MAX, SPECIAL_MAX_BYTES = 64, 32      # limits of bpe_encode_text_gpt4_special
+
+    def encode_text_gpt4(self, data, merges, byte_perm=None, out=None, specials=None):
+        """-> ids int32 of utf-8 `data`: GPT-4 split + encode, both on the GPU (regex.py:111-121).
+        specials: [(utf-8 bytes, id), ...] in the order of the special_tokens dict — their occurrences are found on the
+        GPU as well and every part between them is encoded on its own (regex.py:152-163)."""
         self._ensure_gpt4_tables()
         b = np.frombuffer(data, dtype=np.uint8) if not isinstance(data, np.ndarray) else np.ascontiguousarray(data, dtype=np.uint8)
         m = np.ascontiguousarray(np.asarray(merges, dtype=np.int32).reshape(-1, 2))
@@ -228,6 +233,15 @@ class Engine:
         if out is None:
             out = np.empty(max(b.size, 1), dtype=np.int32)
         n = ctypes.c_uint64()
+        if specials:
+            blob = np.frombuffer(b"".join(t for t, _ in specials), dtype=np.uint8)
+            offs = np.zeros(len(specials) + 1, dtype=np.uint32)
+            np.cumsum([len(t) for t, _ in specials], out=offs[1:])
+            ids = np.asarray([i for _, i in specials], dtype=np.int32)
+            self._check(self._lib.bpe_encode_text_gpt4_special(
+                self._h, _ptr(b) if b.size else None, b.size, _ptr(m) if m.size else None, m.shape[0], _ptr(perm),
+                _ptr(blob), _ptr(offs), _ptr(ids), len(specials), _ptr(out), out.size, ctypes.byref(n)), "bpe_encode_text_gpt4_special")
+            return out[: n.value]
         self._check(self._lib.bpe_encode_text_gpt4(self._h, _ptr(b) if b.size else None, b.size, _ptr(m) if m.size else None,
                                                    m.shape[0], _ptr(perm), _ptr(out), out.size, ctypes.byref(n)), "bpe_encode_text_gpt4")
         return out[: n.value]

@@ -317,6 +317,13 @@ class RegexTokenizer(Tokenizer):
         # `pattern` string, which load() may have replaced
         return self.compiled_pattern.pattern == GPT4_SPLIT_PATTERN and nbytes >= self.DEVICE_SPLIT_MIN_BYTES
 
+    def _device_specials(self, special):
+        """The device front end takes at most 64 specials of 1..32 utf-8 bytes and non-negative int32 ids; anything else
+        keeps the reference's host split (below)."""
+        E = Engine
+        return (0 < len(special) <= E.SPECIAL_MAX and
+                all(isinstance(k, str) and 0 < len(k.encode("utf-8")) <= E.SPECIAL_MAX_BYTES and 0 <= int(v) < 2 ** 31 for k, v in special.items()))
+
     def train(self, text, vocab_size, verbose=False, *, resume=False):
         assert vocab_size >= 256
         data = text.encode("utf-8")
@@ -394,6 +401,13 @@ class RegexTokenizer(Tokenizer):
             raise ValueError(f"allowed_special={allowed_special} not understood")
         if not special:
             return self.encode_ordinary(text)
+        if self.merges and self._device_specials(special):
+            raw = text.encode("utf-8")
+            if self._device_split(len(raw)):
+                # regex.py:152-163 on the GPU: the specials are found there, every part between them is split and encoded
+                # on its own, one call (k_special.cuh)
+                spec = [(k.encode("utf-8"), int(v)) for k, v in special.items()]
+                return self.engine.encode_text_gpt4(raw, self._merge_array(), specials=spec).tolist()
         splitter = "(" + "|".join(re.escape(k) for k in special) + ")"
         ids = []
         for part in re.split(splitter, text):

@@ -46,9 +46,10 @@ def jobs():
     lib = build_emu.build()
     t = lambda f: os.path.join("tests", f)  # noqa: E731
     procs = {
-        # round-2 kernels that have not run on a GPU yet — memoised chunk encode (k_encode2.cuh), bpe_replay / resume —
-        # and bpe_decode
-        "new_kernels": _pytest(lib, [t("test_gpu_zy_encode2.py"), t("test_gpu_zz_resume.py"), t("test_gpu_zz_file.py"), t("test_gpu_decode.py")]),
+        # round-2 kernels that have not run on a GPU yet — memoised chunk encode (k_encode2.cuh), bpe_replay / resume, the
+        # special-token front end (k_special.cuh), file / shard entry points — and bpe_decode
+        "new_kernels": _pytest(lib, [t("test_gpu_zy_encode2.py"), t("test_gpu_zz_resume.py"), t("test_gpu_zz_file.py"), t("test_gpu_zz_special.py"),
+                                       t("test_gpu_decode.py")]),
         # kernels already validated on B200s, as a check of the emulator itself (golden vectors of the reference)
         "validated_kernels": _pytest(lib, [t("test_gpu_parity.py")],
                                      "wikipedia or taylorswift or small_cases or primitives or long_runs or table_growth or rescan"),

@@ -102,3 +102,54 @@ def test_product_rule_code_on_cpu(taylorswift):
     check_bytes(taylorswift, (0, 5, 2048, 4096))
     from minbpe_b200.synth import generate
     check_bytes(generate(1337, 2 << 20).tobytes().decode("utf-8"), (4096,))
+
+
+def test_product_rule_code_with_special_token_boundaries():
+    """regex.py:152-163: the text is cut at the special tokens first (re.split, leftmost, first alternative wins, no
+    overlaps) and every part is split by the GPT-4 pattern ON ITS OWN.  The device does it in one pass: the bytes of every
+    occurrence get the boundary class SC_B and the WITH_B instantiation of split_logic.h treats them as end / start of
+    text.  Pinned here against `regex` on random adversarial texts with specials sprinkled in — including specials that
+    begin or end with a space, a letter, an apostrophe or a digit, adjacent specials, and specials at either end."""
+    import numpy as np
+
+    import oracle
+    from minbpe_b200.unicode_tables import tables
+    cls, contr = tables()
+    rnd = random.Random(777)
+    alphabet = list("ab'sSdDmMtTlLvVeErR 12\t\n\r!.,' 　é日ſ½") + ["  ", "\n\n", "'ll", "'ve", " '", "K", "\U0001f600"]
+    special_sets = [["<|endoftext|>"], ["<|a|>", "<|ab|>", "|>"], [" <s> ", "'s", "12"], ["x", "日"], ["\n<eot>\n", "  "], ["a b", "b a"]]
+
+    def expected(text, specials):
+        pat = "(" + "|".join(regex.escape(k) for k in specials) + ")"
+        offs, hits, pos = [], [], 0
+        for part in regex.split(pat, text):
+            nb = len(part.encode("utf-8"))
+            if part in specials:
+                offs.append(pos)
+                hits.append((pos, nb))
+            else:
+                p = pos
+                for ch in GPT4.findall(part):
+                    offs.append(p)
+                    p += len(ch.encode("utf-8"))
+            pos += nb
+        return np.asarray(offs, dtype=np.uint64), hits
+
+    n_hits = 0
+    for it in range(5000):
+        specials = rnd.choice(special_sets)
+        parts = []
+        for _ in range(rnd.randint(1, 5)):
+            parts.append("".join(rnd.choice(alphabet) for _ in range(rnd.randint(0, 12))))
+            if rnd.random() < 0.8:
+                parts.append(rnd.choice(specials))
+        text = "".join(parts)
+        if not text:
+            continue
+        want, hits = expected(text, specials)
+        n_hits += len(hits)
+        data = text.encode("utf-8")
+        for tile in (0, rnd.randint(1, 9)):
+            got = oracle.split_logic_offsets_special(data, cls, contr, hits, tile)
+            assert np.array_equal(got, want), (text, specials, tile, got.tolist(), want.tolist())
+    assert n_hits > 5000
