@@ -72,6 +72,7 @@ struct bpe_handle {
     int opt_kernel_timing = 0, opt_rescan = 0, opt_batch = 256, opt_table_log2 = 0;
     int opt_memo_log2 = 0;   // BPE_OPT_ENC_MEMO_LOG2 (test hook): log2 slots of the encode memo table, 0 = default
     u32 opt_vocab_cap = 0;   // BPE_OPT_VOCAB_CAP: lower bound of the delta-vector layout V used by bpe_train
+    int opt_split_pattern = 0;   // BPE_OPT_SPLIT_PATTERN: 0 = GPT-4 split pattern, 1 = GPT-2 (bpe_split_gpt4 / bpe_load_text_gpt4 / bpe_encode_text_gpt4*)
 
     bpe_timing tm = {};
     std::vector<cudaEvent_t> ev_pool;  // per-launch timing of the fused merge kernel (BPE_OPT_KERNEL_TIMING)
@@ -233,6 +234,9 @@ extern "C" int bpe_set_option(bpe_handle *h, int opt, int64_t value) {
             cudaSetDevice(h->device); cudaStreamSynchronize(h->stream);
             enc2_free(h);   // re-created with the new size by the next encode call
             break;
+        case BPE_OPT_SPLIT_PATTERN:
+            if (value != 0 && value != 1) return fail(h, BPE_ERR_ARG, "split pattern must be 0 (GPT-4) or 1 (GPT-2)");
+            h->opt_split_pattern = (int)value; break;
         case BPE_OPT_SPLIT_PIECE:
             if (value != 0 && value < 4096) return fail(h, BPE_ERR_ARG, "split piece must be 0 (default) or >= 4096 bytes");
             g_split_piece_override = (u64)value; break;

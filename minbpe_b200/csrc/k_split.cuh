@@ -117,7 +117,8 @@ __global__ void __launch_bounds__(1024) k_split_scan_parts(SplFwd *__restrict__ 
 }
 
 // per tile: scans + rule.  TOKENS = false: flag[i] = 1 at chunk starts.  TOKENS = true: dst[i] = byte | chunk mark.
-template <bool TOKENS, bool WITH_B>
+// PATTERN: 0 = the GPT-4 split pattern, 1 = the GPT-2 one (split_logic.h: same scans, another rule).
+template <bool TOKENS, bool WITH_B, int PATTERN>
 __global__ void __launch_bounds__(SP_THREADS) k_split_apply(const unsigned char *__restrict__ b, const unsigned char *__restrict__ meta, u64 n,
                                                             const unsigned char *__restrict__ contr,
                                                             const SplFwd *__restrict__ fpart, const SplBwd *__restrict__ bpart,
@@ -174,7 +175,8 @@ __global__ void __launch_bounds__(SP_THREADS) k_split_apply(const unsigned char 
         const SplFwd fprev = frun;
         frun = spl_fwd_combine(frun, fe[k]);
         bool st = false;
-        if (i < n && (mm[k] & SM_START)) st = spl_chunk_start<WITH_B>(i, n, frun, fprev, gi[k], B, M, contr);
+        if (i < n && (mm[k] & SM_START))
+            st = PATTERN == 1 ? spl_chunk_start_gpt2<WITH_B>(i, n, frun, gi[k], B, M) : spl_chunk_start<WITH_B>(i, n, frun, fprev, gi[k], B, M, contr);
         out[k] = TOKENS ? ((u32)s_b[SP_HALO + tid * SP_ITEMS + k] | (st ? TOK_FLAG : 0u)) : (st ? 1u : 0u);
     }
     if (TOKENS) {

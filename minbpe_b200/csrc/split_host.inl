@@ -76,14 +76,20 @@ static int split_run(bpe_handle *h, const uint8_t *bytes, u64 n, SplitWork &W, u
     if (with_b) {
         k_split_reduce<true><<<ntiles, SP_THREADS, 0, h->stream>>>(W.meta, n, W.fpart, W.bpart);
         k_split_scan_parts<<<1, 1024, 0, h->stream>>>(W.fpart, W.bpart, ntiles);
-        k_split_apply<false, true><<<ntiles, SP_THREADS, 0, h->stream>>>(W.bytes, W.meta, n, h->d_contr, W.fpart, W.bpart, W.flag, nullptr);
+        if (h->opt_split_pattern == 1) k_split_apply<false, true, 1><<<ntiles, SP_THREADS, 0, h->stream>>>(W.bytes, W.meta, n, h->d_contr, W.fpart, W.bpart, W.flag, nullptr);
+        else k_split_apply<false, true, 0><<<ntiles, SP_THREADS, 0, h->stream>>>(W.bytes, W.meta, n, h->d_contr, W.fpart, W.bpart, W.flag, nullptr);
         k_special_flags<<<grid_for(hits->size(), 256, h->sms * 8), 256, 0, h->stream>>>(W.flag, h->spec->d_hit, hits->size(), n);
         h->tm.kernel_launches += 1;
     } else {
         k_split_reduce<false><<<ntiles, SP_THREADS, 0, h->stream>>>(W.meta, n, W.fpart, W.bpart);
         k_split_scan_parts<<<1, 1024, 0, h->stream>>>(W.fpart, W.bpart, ntiles);
-        if (tokens) k_split_apply<true, false><<<ntiles, SP_THREADS, 0, h->stream>>>(W.bytes, W.meta, n, h->d_contr, W.fpart, W.bpart, nullptr, tokens);
-        else k_split_apply<false, false><<<ntiles, SP_THREADS, 0, h->stream>>>(W.bytes, W.meta, n, h->d_contr, W.fpart, W.bpart, W.flag, nullptr);
+        if (h->opt_split_pattern == 1) {
+            if (tokens) k_split_apply<true, false, 1><<<ntiles, SP_THREADS, 0, h->stream>>>(W.bytes, W.meta, n, h->d_contr, W.fpart, W.bpart, nullptr, tokens);
+            else k_split_apply<false, false, 1><<<ntiles, SP_THREADS, 0, h->stream>>>(W.bytes, W.meta, n, h->d_contr, W.fpart, W.bpart, W.flag, nullptr);
+        } else {
+            if (tokens) k_split_apply<true, false, 0><<<ntiles, SP_THREADS, 0, h->stream>>>(W.bytes, W.meta, n, h->d_contr, W.fpart, W.bpart, nullptr, tokens);
+            else k_split_apply<false, false, 0><<<ntiles, SP_THREADS, 0, h->stream>>>(W.bytes, W.meta, n, h->d_contr, W.fpart, W.bpart, W.flag, nullptr);
+        }
     }
     h->tm.kernel_launches += 4;
     if (e0) {   // BPE_OPT_KERNEL_TIMING: device time of the four split kernels -> bpe_timing.init_ms

@@ -202,3 +202,50 @@ SPL_HD bool spl_chunk_start(uint64_t i, uint64_t n, SplFwd f, SplFwd fprev, SplB
     }
     return false;
 }
+
+// ---- the GPT-2 pattern (regex.py:18) on the same scans ------------------------------------------------------------
+//   '(?:[sdmt]|ll|ve|re)| ?\p{L}+| ?\p{N}+| ?[^\s\p{L}\p{N}]+|\s+(?!\S)|\s+
+// Simpler than the GPT-4 one: a run of letters, of digits or of "Oish" characters is one chunk, with a single U+0020 in
+// front joining it; a whitespace run is one chunk, except that its last character is split off when something follows
+// (it joins the next chunk if it is U+0020, stands alone otherwise); contractions are ASCII and case-sensitive, and only
+// tried where the apostrophe is a match start (a one-character Oish run without a space in front).
+template <class Bytes>
+SPL_HD uint32_t spl_contraction_len_gpt2(const Bytes &b, uint64_t n, uint64_t s) {
+    if (s >= n) return 0;
+    const uint32_t c1 = b(s);
+    if (c1 == 's' || c1 == 'd' || c1 == 'm' || c1 == 't') return 2;
+    if (s + 1 >= n) return 0;
+    const uint32_t c2 = b(s + 1);
+    if ((c1 == 'l' && c2 == 'l') || (c1 == 'v' && c2 == 'e') || (c1 == 'r' && c2 == 'e')) return 3;
+    return 0;
+}
+
+template <bool WITH_B = false, class Bytes, class Meta>
+SPL_HD bool spl_chunk_start_gpt2(uint64_t i, uint64_t n, SplFwd f, SplBwd g, const Bytes &b, const Meta &meta) {
+    if (i == 0) return true;
+    const uint32_t cls = meta(i) & SM_CLS, kind = spl_kind(cls);
+    if (WITH_B && cls == SC_B) return false;
+    const uint32_t before = f.since - 1u;            // characters of the run in front of this one
+    if (kind == SC_SP) {
+        if (before == 0u) return true;                                   // \s+(?!\S) / \s+ from the start of the run
+        return g.toend == 1u && !(g.bits & SPL_B_ATEND);                 // the last one is left for what follows
+    }
+    const bool prev_space = spl_is_space20<WITH_B>(b, meta, i - 1);      // it starts the chunk (" ?" prefix)
+    if (kind == SC_N || kind == SC_O) return before == 0u && !prev_space;
+    // letters
+    if (before == 0u) {
+        if (prev_space) return false;
+        const uint64_t p = spl_char_start(b, i - 1);
+        if (b(p) == 0x27u && spl_single_oish_start<WITH_B>(b, meta, n, p, i) && spl_contraction_len_gpt2(b, n, i) != 0u) return false;
+        return true;
+    }
+    if (before <= 2u) {   // second or third letter of a run that follows a contraction apostrophe
+        uint64_t s = i;
+        for (uint32_t c = 0; c < before; ++c) s = spl_char_start(b, s - 1);
+        if (s >= 1 && b(s - 1) == 0x27u && spl_single_oish_start<WITH_B>(b, meta, n, s - 1, s)) {
+            const uint32_t clen = spl_contraction_len_gpt2(b, n, s);
+            return clen != 0u && before == clen - 1u;
+        }
+    }
+    return false;
+}

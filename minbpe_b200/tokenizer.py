@@ -312,10 +312,19 @@ class RegexTokenizer(Tokenizer):
     # regex.findall — tests/test_split_rules.py, tests/test_gpu_split.py); short ones stay on the host
     DEVICE_SPLIT_MIN_BYTES = 1 << 16
 
+    _DEVICE_PATTERNS = {GPT4_SPLIT_PATTERN: 0, GPT2_SPLIT_PATTERN: 1}     # BPE_OPT_SPLIT_PATTERN values
+
     def _device_split(self, nbytes):
+        """Large texts under one of the reference's two patterns (regex.py:18-19) are split on the GPU; the engine may be
+        shared by tokenizers with different patterns, so the pattern is selected before every such call."""
         # the pattern that is actually used for splitting is compiled_pattern (regex.py:32,41,114), not the
         # `pattern` string, which load() may have replaced
-        return self.compiled_pattern.pattern == GPT4_SPLIT_PATTERN and nbytes >= self.DEVICE_SPLIT_MIN_BYTES
+        which = self._DEVICE_PATTERNS.get(self.compiled_pattern.pattern)
+        if which is None or nbytes < self.DEVICE_SPLIT_MIN_BYTES:
+            return False
+        from .engine import OPT_SPLIT_PATTERN
+        self.engine.set_option(OPT_SPLIT_PATTERN, which)
+        return True
 
     def _device_specials(self, special):
         """The device front end takes at most 64 specials of 1..32 utf-8 bytes and non-negative int32 ids; anything else
@@ -339,11 +348,14 @@ class RegexTokenizer(Tokenizer):
         GPU) every rank trains on its own byte range — cut where a letter is followed by a space, a provable chunk
         boundary — and all ranks end with identical merges / vocab.  GPT-4 split pattern only."""
         assert vocab_size >= 256
-        if self.compiled_pattern.pattern != GPT4_SPLIT_PATTERN:
-            raise ValueError("train_from_file splits on the device and supports the GPT-4 split pattern only; "
+        which = self._DEVICE_PATTERNS.get(self.compiled_pattern.pattern)
+        if which is None:
+            raise ValueError("train_from_file splits on the device and supports the GPT-2 / GPT-4 split patterns only; "
                              "use train(open(path).read(), ...) for other patterns")
         from .dist import train_file
+        from .engine import OPT_SPLIT_PATTERN
         eng = self.engine
+        eng.set_option(OPT_SPLIT_PATTERN, which)
         pairs, counts, done = train_file(eng, eng.device, path, vocab_size - 256, group=group)
         self.last_timing = eng.timing()
         self._adopt(pairs, counts, done, vocab_size - 256, verbose)

@@ -16,7 +16,7 @@ struct ByteAcc {
 
 // hits[j] = position << 8 | length of a special-token occurrence (WITH_B only): its bytes get the boundary class SC_B
 // before the scans, exactly as k_special_meta does, and the flags are fixed up as k_special_flags does.
-template <bool WITH_B>
+template <bool WITH_B, int PATTERN = 0>   // PATTERN: 0 = GPT-4, 1 = GPT-2 (split_logic.h)
 static int flags_impl(const uint8_t *bytes, uint64_t n, const uint8_t *cls_table, const uint8_t *contr, uint64_t tile,
                       const uint64_t *hits, uint64_t n_hits, uint8_t *flags) {
     if (n == 0) return 0;
@@ -58,7 +58,8 @@ static int flags_impl(const uint8_t *bytes, uint64_t n, const uint8_t *cls_table
         for (uint64_t i = hi; i > lo; --i) { g = spl_bwd_combine(spl_bwd_elem<WITH_B>(i - 1, n, meta[i - 1], i < n ? meta[i] : 0), g); gv[i - 1 - lo] = g; }
         for (uint64_t i = lo; i < hi; ++i) {
             const SplFwd fprev = (i == lo) ? fcar[t] : fv[i - 1 - lo];
-            flags[i] = (meta[i] & SM_START) && spl_chunk_start<WITH_B>(i, n, fv[i - lo], fprev, gv[i - lo], B, M, contr) ? 1 : 0;
+            if (PATTERN == 1) flags[i] = (meta[i] & SM_START) && spl_chunk_start_gpt2<WITH_B>(i, n, fv[i - lo], gv[i - lo], B, M) ? 1 : 0;
+            else flags[i] = (meta[i] & SM_START) && spl_chunk_start<WITH_B>(i, n, fv[i - lo], fprev, gv[i - lo], B, M, contr) ? 1 : 0;
         }
     }
     if (WITH_B)
@@ -80,4 +81,11 @@ extern "C" int split_logic_flags(const uint8_t *bytes, uint64_t n, const uint8_t
 extern "C" int split_logic_flags_special(const uint8_t *bytes, uint64_t n, const uint8_t *cls_table, const uint8_t *contr,
                                          uint64_t tile, const uint64_t *hits, uint64_t n_hits, uint8_t *flags) {
     return flags_impl<true>(bytes, n, cls_table, contr, tile, hits, n_hits, flags);
+}
+
+// GPT-2 pattern (regex.py:18), plain and with special-token boundaries
+extern "C" int split_logic_flags_gpt2(const uint8_t *bytes, uint64_t n, const uint8_t *cls_table, const uint8_t *contr,
+                                      uint64_t tile, const uint64_t *hits, uint64_t n_hits, uint8_t *flags) {
+    if (n_hits) return flags_impl<true, 1>(bytes, n, cls_table, contr, tile, hits, n_hits, flags);
+    return flags_impl<false, 1>(bytes, n, cls_table, contr, tile, nullptr, 0, flags);
 }

@@ -153,3 +153,60 @@ def test_product_rule_code_with_special_token_boundaries():
             got = oracle.split_logic_offsets_special(data, cls, contr, hits, tile)
             assert np.array_equal(got, want), (text, specials, tile, got.tolist(), want.tolist())
     assert n_hits > 5000
+
+
+GPT2 = regex.compile(r"""'(?:[sdmt]|ll|ve|re)| ?\p{L}+| ?\p{N}+| ?[^\s\p{L}\p{N}]+|\s+(?!\S)|\s+""")
+
+
+def test_product_rule_code_gpt2_pattern(taylorswift):
+    """The GPT-2 split pattern (regex.py:18) from the same scans (spl_chunk_start_gpt2), plain and with special-token
+    boundaries, against `regex`."""
+    import numpy as np
+
+    import oracle
+    from minbpe_b200.unicode_tables import tables
+    cls, contr = tables()
+
+    def check_bytes(text, tiles):
+        data, offs = oracle.split_to_stream(text, GPT2)
+        for tile in tiles:
+            got = oracle.split_logic_offsets_gpt2(data.tobytes(), cls, contr, (), tile)
+            assert np.array_equal(got, offs), (text[:80], tile, got.tolist()[:20], offs.tolist()[:20])
+
+    for t in CASES:
+        if t:
+            check_bytes(t, (0, 1, 3, 7, 64))
+    rnd = random.Random(2024)
+    alphabet = list("ab'sSdDmMtTlLvVeErR 12\t\n\r!.,' 　é日ſ½") + ["  ", "\n\n", "'ll", "'ve", " '", "K", "\U0001f600", "'re", "'LL"]
+    for _ in range(6000):
+        check_bytes("".join(rnd.choice(alphabet) for _ in range(rnd.randint(1, 24))), (0, rnd.randint(1, 9)))
+    check_bytes(taylorswift, (0, 5, 4096))
+    from minbpe_b200.synth import generate
+    check_bytes(generate(1337, 1 << 20).tobytes().decode("utf-8"), (4096,))
+    # with specials as boundaries
+    special_sets = [["<|endoftext|>"], ["<|a|>", "<|ab|>", "|>"], [" <s> ", "'s", "12"], ["x", "日"], ["\n<eot>\n", "  "], ["a b", "b a"]]
+    for it in range(3000):
+        specials = rnd.choice(special_sets)
+        parts = []
+        for _ in range(rnd.randint(1, 5)):
+            parts.append("".join(rnd.choice(alphabet) for _ in range(rnd.randint(0, 12))))
+            if rnd.random() < 0.8:
+                parts.append(rnd.choice(specials))
+        text = "".join(parts)
+        if not text:
+            continue
+        pat = "(" + "|".join(regex.escape(k) for k in specials) + ")"
+        offs, hits, pos = [], [], 0
+        for part in regex.split(pat, text):
+            nb = len(part.encode("utf-8"))
+            if part in specials:
+                offs.append(pos)
+                hits.append((pos, nb))
+            else:
+                p = pos
+                for ch in GPT2.findall(part):
+                    offs.append(p)
+                    p += len(ch.encode("utf-8"))
+            pos += nb
+        got = oracle.split_logic_offsets_gpt2(text.encode("utf-8"), cls, contr, hits, rnd.choice((0, 3, 8)))
+        assert np.array_equal(got, np.asarray(offs, dtype=np.uint64)), (text, specials)
