@@ -103,6 +103,7 @@ class Tokenizer:
         self.vocab = self._build_vocab()
         self._device = device
         self._engine = None
+        self._byte_perm = None     # 256-entry byte permutation applied before the merges (GPT4Tokenizer, gpt4.py:76-77)
 
     # -- device plumbing (not part of the reference API) --
     @property
@@ -268,7 +269,7 @@ class BasicTokenizer(Tokenizer):
         data = text.encode("utf-8")
         if len(data) < 2 or not self.merges:
             return list(data)
-        return self.engine.encode(data, None, self._merge_array()).tolist()
+        return self.engine.encode(data, None, self._merge_array(), self._byte_perm).tolist()
 
 
 def split_text(compiled_pattern, text):
@@ -384,19 +385,21 @@ class RegexTokenizer(Tokenizer):
 
     def _encode_chunk(self, text_bytes):
         """regex.py:92-109 for a single chunk."""
-        if len(text_bytes) < 2 or not self.merges:
+        if not self.merges or (len(text_bytes) < 2 and self._byte_perm is None):
             return list(text_bytes)
-        return self.engine.encode(bytes(text_bytes), None, self._merge_array()).tolist()
+        return self.engine.encode(bytes(text_bytes), None, self._merge_array(), self._byte_perm).tolist()
 
     def encode_ordinary(self, text):
         """regex.py:111-121."""
         raw = text.encode("utf-8")
         if self.merges and self._device_split(len(raw)):
-            return self.engine.encode_text_gpt4(raw, self._merge_array()).tolist()   # split + encode on the device, no offsets
+            return self.engine.encode_text_gpt4(raw, self._merge_array(), self._byte_perm).tolist()   # split + encode on the device, no offsets
         data, offsets = split_text(self.compiled_pattern, text)
-        if not self.merges or len(data) < 2:
+        if not self.merges or (len(data) < 2 and self._byte_perm is None):
             return list(data)
-        return self.engine.encode(data, offsets, self._merge_array()).tolist()
+        if not len(data):
+            return []
+        return self.engine.encode(data, offsets, self._merge_array(), self._byte_perm).tolist()
 
     def encode(self, text, allowed_special="none_raise"):
         """regex.py:123-164."""
@@ -419,7 +422,7 @@ class RegexTokenizer(Tokenizer):
                 # regex.py:152-163 on the GPU: the specials are found there, every part between them is split and encoded
                 # on its own, one call (k_special.cuh)
                 spec = [(k.encode("utf-8"), int(v)) for k, v in special.items()]
-                return self.engine.encode_text_gpt4(raw, self._merge_array(), specials=spec).tolist()
+                return self.engine.encode_text_gpt4(raw, self._merge_array(), self._byte_perm, specials=spec).tolist()
         splitter = "(" + "|".join(re.escape(k) for k in special) + ")"
         ids = []
         for part in re.split(splitter, text):
