@@ -412,8 +412,10 @@ extern "C" int bpe_encode_stats(bpe_handle *h, uint64_t *out /* [8] */) {
     return BPE_OK;
 }
 
-// regex.py:92-121 / basic.py:57-74.  Chunked input (RegexTokenizer, any pattern: the caller brings the offsets) goes
-// through the memoised kernels; a single chunk (BasicTokenizer) through the general path.
+// regex.py:92-121 / basic.py:57-74.  Chunked input (RegexTokenizer, any pattern: the caller brings the offsets) of at
+// least ENC2_MIN_BYTES goes through the memoised kernels; short inputs (a chunk, a sentence: the memo's 0.5 GB of state
+// and its reset on every change of merges buy nothing there) and a single chunk (BasicTokenizer) take the general path.
+#define ENC2_MIN_BYTES (1u << 16)
 extern "C" int bpe_encode(bpe_handle *h, const uint8_t *bytes, uint64_t n, const uint64_t *chunk_offsets,
                           uint64_t n_chunks, const int32_t *merges, int32_t n_merges, const uint8_t *byte_perm,
                           int32_t *out_ids, uint64_t out_cap, uint64_t *out_n) {
@@ -426,7 +428,7 @@ extern "C" int bpe_encode(bpe_handle *h, const uint8_t *bytes, uint64_t n, const
     if (rc) return rc;
     *out_n = 0;
     h->tm.h2d_bytes = 0; h->tm.d2h_bytes = 0; h->tm.kernel_launches = 0;
-    if (n >= 1 && n_merges > 0 && chunk_offsets && n_chunks >= 1)
+    if (n >= ENC2_MIN_BYTES && n_merges > 0 && chunk_offsets && n_chunks >= 1)
         return encode_with_offsets(h, bytes, n, chunk_offsets, n_chunks, merges, n_merges, byte_perm, out_ids, out_cap, out_n);
     return encode_general(h, bytes, n, chunk_offsets, n_chunks, merges, n_merges, byte_perm, out_ids, out_cap, out_n);
 }
