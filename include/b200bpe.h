@@ -144,8 +144,9 @@ int bpe_encode_text_gpt4_special(bpe_handle *h, const uint8_t *bytes, uint64_t n
 /* Counters of the memoised encode: out[0] distinct chunks in the memo table, [1] ids in its pool; of the last call:
  * [2] chunks newly added, [3] chunks encoded directly (no room in the table, or longer than 32 bytes), [4] of which
  * long, [5] pieces, [6] pieces that took the general path, [7] device microseconds of the encode kernels
- * (BPE_OPT_KERNEL_TIMING). */
-int bpe_encode_stats(bpe_handle *h, uint64_t *out /* [8] */);
+ * (BPE_OPT_KERNEL_TIMING), [8] pieces done twice because the per-piece id area had to grow, [9] ids of the directly
+ * encoded chunks of the last piece. */
+int bpe_encode_stats(bpe_handle *h, uint64_t *out /* [10] */);
 
 /* ---- the GPT-4 split pattern on the device (regex.py:19, used at regex.py:41 and :114) -------- */
 /* `re.findall(GPT4_SPLIT_PATTERN, text)` as scans + element-wise kernels (k_split.cuh; the rules are

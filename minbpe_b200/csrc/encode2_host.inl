@@ -10,6 +10,7 @@ struct EncState {
     unsigned char *d_perm = nullptr;
     MemoSlot *memo = nullptr; u64 memo_cap = 0;
     u32 *pool = nullptr; u64 pool_cap = 0;
+    u32 *tmp = nullptr; u64 tmp_cap = 0;          // per-piece id area (direct chunks)
     u32 *new_list = nullptr;
     u64 *direct_list = nullptr; u64 direct_cap = 0;
     PosSlot *posmap = nullptr; u64 pos_cap = 0;
@@ -18,7 +19,7 @@ struct EncState {
     int *d_ids = nullptr; u64 ids_cap = 0;
     u64 *d_offs = nullptr; u64 offs_cap = 0;     // staging of host chunk offsets (bpe_encode with offsets)
     // statistics of the last call (bpe_encode_stats)
-    u64 st_chunks_new = 0, st_direct = 0, st_long = 0, st_pieces = 0, st_fallbacks = 0;
+    u64 st_chunks_new = 0, st_direct = 0, st_long = 0, st_pieces = 0, st_fallbacks = 0, st_retries = 0, st_tmp_ids = 0;
     double st_kernel_ms = 0;
 };
 
@@ -35,7 +36,7 @@ static u64 fnv64(const void *p, size_t n) {
 static void enc2_free(bpe_handle *h) {
     EncState *S = h->enc;
     if (!S) return;
-    cudaFree(S->d_merges); cudaFree(S->d_rkeys); cudaFree(S->d_rranks); cudaFree(S->d_perm); cudaFree(S->memo); cudaFree(S->pool);
+    cudaFree(S->d_merges); cudaFree(S->d_rkeys); cudaFree(S->d_rranks); cudaFree(S->d_perm); cudaFree(S->memo); cudaFree(S->pool); cudaFree(S->tmp);
     cudaFree(S->new_list); cudaFree(S->direct_list); cudaFree(S->posmap); cudaFree(S->ctl); cudaFree(S->part); cudaFree(S->excl);
     cudaFree(S->d_total); cudaFree(S->d_ids); cudaFree(S->d_offs);
     delete S;
@@ -49,6 +50,7 @@ static Enc2 enc2_args(const EncState *S) {
     E.text = nullptr; E.flag = nullptr; E.n = 0;
     E.memo = S->memo; E.memo_mask = S->memo_cap - 1; E.memo_limit = S->memo_cap / 2;
     E.pool = S->pool; E.pool_cap = S->pool_cap;
+    E.tmp = S->tmp; E.tmp_cap = S->tmp_cap;
     E.new_list = S->new_list; E.new_cap = (u32)S->memo_cap;
     E.direct_list = S->direct_list; E.direct_cap = S->direct_cap;
     E.posmap = nullptr; E.pos_mask = 0;
@@ -133,59 +135,89 @@ static int enc2_piece(bpe_handle *h, const unsigned char *d_text, const unsigned
         E2CU(cudaMalloc(&S->direct_list, dcap * 8));
         S->direct_cap = dcap;
     }
-    // per-piece counters
-    EncCtl hc;
-    E2CU(cudaMemcpyAsync(&hc, S->ctl, sizeof(EncCtl), cudaMemcpyDeviceToHost, h->stream));
-    E2CU(cudaStreamSynchronize(h->stream));
-    hc.n_new = 0; hc.n_direct = 0; hc.n_long = 0; hc.fail = 0;
-    E2CU(cudaMemcpyAsync(S->ctl, &hc, sizeof(EncCtl), cudaMemcpyHostToDevice, h->stream));
-
-    Enc2 E = enc2_args(S);
-    E.text = d_text; E.flag = d_flag; E.n = m;
+    // per-piece id area for the direct chunks: a guess first (an eighth of the bytes), the worst case (one id per byte)
+    // if the guess turns out too small
+    {
+        const u64 floor_ids = h->opt_memo_log2 ? 1024 : (1ull << 22);      // the test hook also shrinks this
+        const u64 want = std::max<u64>(floor_ids, m / 8);
+        if (S->tmp_cap < want) {
+            cudaFree(S->tmp); S->tmp = nullptr; S->tmp_cap = 0;
+            E2CU(cudaMalloc(&S->tmp, want * 4));
+            S->tmp_cap = want;
+        }
+    }
     const RankTable rt = {S->d_rkeys, S->d_rranks, S->rt_cap - 1};
     const unsigned char *perm = S->has_perm ? S->d_perm : nullptr;
     cudaEvent_t e0 = nullptr, e1 = nullptr;
     if (h->opt_kernel_timing) { cudaEventCreate(&e0); cudaEventCreate(&e1); cudaEventRecord(e0, h->stream); }
-
-    k_enc_insert<<<ntiles, E2_THREADS, 0, h->stream>>>(E);
-    E2CU(cudaMemcpyAsync(&hc, S->ctl, sizeof(EncCtl), cudaMemcpyDeviceToHost, h->stream));
-    E2CU(cudaStreamSynchronize(h->stream));
-    h->tm.kernel_launches += 1;
-    bool bad = hc.fail != 0;
-    if (!bad && hc.n_new) {
-        k_enc_distinct<<<(hc.n_new + 127) / 128, 128, 0, h->stream>>>(E, rt, perm);
-        h->tm.kernel_launches += 1;
-    }
-    if (!bad && hc.n_direct) {
-        const u64 pcap = next_pow2(std::max<u64>(1024, 2 * hc.n_direct));
-        if (pcap > S->pos_cap) {
-            cudaFree(S->posmap); S->posmap = nullptr; S->pos_cap = 0;
-            E2CU(cudaMalloc(&S->posmap, pcap * sizeof(PosSlot)));
-            S->pos_cap = pcap;
-        }
-        E2CU(cudaMemsetAsync(S->posmap, 0, pcap * sizeof(PosSlot), h->stream));
-        E.posmap = S->posmap; E.pos_mask = pcap - 1;
-        if (hc.n_direct > hc.n_long) {
-            k_enc_direct_short<<<(unsigned)((hc.n_direct + 127) / 128), 128, 0, h->stream>>>(E, rt, perm);
-            h->tm.kernel_launches += 1;
-        }
-        if (hc.n_long) {
-            E2CU(cudaFuncSetAttribute(k_enc_direct_long, cudaFuncAttributeMaxDynamicSharedMemorySize, 2 * ENC_LONG_MAX * 4));
-            k_enc_direct_long<<<(unsigned)std::min<u64>(hc.n_direct, (u64)h->sms * 2), 256, 2 * ENC_LONG_MAX * 4, h->stream>>>(E, rt, perm);
-            h->tm.kernel_launches += 1;
-        }
-    }
-    u64 total = 0;
-    if (!bad) {
-        k_enc_count<<<ntiles, E2_THREADS, 0, h->stream>>>(E, S->part);
-        k_flag_scan_parts<<<1, 1024, 0, h->stream>>>(S->part, S->excl, ntiles, S->d_total);
-        h->tm.kernel_launches += 2;
-        EncCtl hc2;
-        E2CU(cudaMemcpyAsync(&total, S->d_total, 8, cudaMemcpyDeviceToHost, h->stream));
-        E2CU(cudaMemcpyAsync(&hc2, S->ctl, sizeof(EncCtl), cudaMemcpyDeviceToHost, h->stream));
+    EncCtl hc;
+    Enc2 E;
+    bool bad = false;
+    u64 total = 0, n_new_all = 0;
+    for (int attempt = 0;; ++attempt) {
+        // per-piece counters
+        E2CU(cudaMemcpyAsync(&hc, S->ctl, sizeof(EncCtl), cudaMemcpyDeviceToHost, h->stream));
         E2CU(cudaStreamSynchronize(h->stream));
-        bad = hc2.fail != 0;
+        hc.n_new = 0; hc.n_direct = 0; hc.n_long = 0; hc.fail = 0; hc.tmp_used = 0;
+        E2CU(cudaMemcpyAsync(S->ctl, &hc, sizeof(EncCtl), cudaMemcpyHostToDevice, h->stream));
+        E = enc2_args(S);
+        E.text = d_text; E.flag = d_flag; E.n = m;
+
+        k_enc_insert<<<ntiles, E2_THREADS, 0, h->stream>>>(E);
+        E2CU(cudaMemcpyAsync(&hc, S->ctl, sizeof(EncCtl), cudaMemcpyDeviceToHost, h->stream));
+        E2CU(cudaStreamSynchronize(h->stream));
+        h->tm.kernel_launches += 1;
+        n_new_all += hc.n_new;
+        bad = hc.fail != 0;
+        if (!bad && hc.n_new) {
+            k_enc_distinct<<<(hc.n_new + 127) / 128, 128, 0, h->stream>>>(E, rt, perm);
+            h->tm.kernel_launches += 1;
+        }
+        if (!bad && hc.n_direct) {
+            const u64 pcap = next_pow2(std::max<u64>(1024, 2 * hc.n_direct));
+            if (pcap > S->pos_cap) {
+                cudaFree(S->posmap); S->posmap = nullptr; S->pos_cap = 0;
+                E2CU(cudaMalloc(&S->posmap, pcap * sizeof(PosSlot)));
+                S->pos_cap = pcap;
+            }
+            E2CU(cudaMemsetAsync(S->posmap, 0, pcap * sizeof(PosSlot), h->stream));
+            E.posmap = S->posmap; E.pos_mask = pcap - 1;
+            if (hc.n_direct > hc.n_long) {
+                k_enc_direct_short<<<(unsigned)((hc.n_direct + 127) / 128), 128, 0, h->stream>>>(E, rt, perm);
+                h->tm.kernel_launches += 1;
+            }
+            if (hc.n_long) {
+                E2CU(cudaFuncSetAttribute(k_enc_direct_long, cudaFuncAttributeMaxDynamicSharedMemorySize, 2 * ENC_LONG_MAX * 4));
+                k_enc_direct_long<<<(unsigned)std::min<u64>(hc.n_direct, (u64)h->sms * 2), 256, 2 * ENC_LONG_MAX * 4, h->stream>>>(E, rt, perm);
+                h->tm.kernel_launches += 1;
+            }
+        }
+        u32 fail_bits = hc.fail;
+        total = 0;
+        if (!bad) {
+            k_enc_count<<<ntiles, E2_THREADS, 0, h->stream>>>(E, S->part);
+            k_flag_scan_parts<<<1, 1024, 0, h->stream>>>(S->part, S->excl, ntiles, S->d_total);
+            h->tm.kernel_launches += 2;
+            EncCtl hc2;
+            E2CU(cudaMemcpyAsync(&total, S->d_total, 8, cudaMemcpyDeviceToHost, h->stream));
+            E2CU(cudaMemcpyAsync(&hc2, S->ctl, sizeof(EncCtl), cudaMemcpyDeviceToHost, h->stream));
+            E2CU(cudaStreamSynchronize(h->stream));
+            fail_bits = hc2.fail;
+            bad = fail_bits != 0;
+            S->st_tmp_ids = hc2.tmp_used;
+        }
+        // only the per-piece area was too small (a chunk that went unresolved for that reason raised the other bit as
+        // well: k_enc_count): every memo entry of this attempt is complete, so the piece can simply be done again
+        if (bad && (fail_bits & E2_FAIL_TMP) && attempt == 0 && S->tmp_cap < m) {
+            cudaFree(S->tmp); S->tmp = nullptr; S->tmp_cap = 0;
+            E2CU(cudaMalloc(&S->tmp, m * 4));
+            S->tmp_cap = m;
+            S->st_retries += 1;
+            continue;
+        }
+        break;
     }
+    hc.n_new = (u32)n_new_all;
     S->st_chunks_new += hc.n_new; S->st_direct += hc.n_direct; S->st_long += hc.n_long; S->st_pieces += 1;
     if (bad) {
         // something did not fit (id pool, lists, an oversize chunk, a tag collision): start the memo afresh for
@@ -296,7 +328,7 @@ static int encode_text_impl(bpe_handle *h, const uint8_t *bytes, uint64_t n, con
     int rc = enc2_prepare(h, merges, n_merges, byte_perm, use_spec);
     if (rc) return rc;
     EncState *S = h->enc;
-    S->st_chunks_new = S->st_direct = S->st_long = S->st_pieces = S->st_fallbacks = 0; S->st_kernel_ms = 0;
+    S->st_chunks_new = S->st_direct = S->st_long = S->st_pieces = S->st_fallbacks = S->st_retries = 0; S->st_kernel_ms = 0;
     const u64 piece = g_split_piece_override ? g_split_piece_override : SPLIT_PIECE_BYTES;
     u64 written = 0;
     std::vector<u64> hits;
@@ -349,7 +381,7 @@ static int encode_with_offsets(bpe_handle *h, const uint8_t *bytes, uint64_t n, 
     int rc = enc2_prepare(h, merges, n_merges, byte_perm);
     if (rc) return rc;
     EncState *S = h->enc;
-    S->st_chunks_new = S->st_direct = S->st_long = S->st_pieces = S->st_fallbacks = 0; S->st_kernel_ms = 0;
+    S->st_chunks_new = S->st_direct = S->st_long = S->st_pieces = S->st_fallbacks = S->st_retries = 0; S->st_kernel_ms = 0;
     const u64 piece = g_split_piece_override ? g_split_piece_override : SPLIT_PIECE_BYTES;
     u64 written = 0;
     u64 c0 = 0;
@@ -401,7 +433,7 @@ static int encode_with_offsets(bpe_handle *h, const uint8_t *bytes, uint64_t n, 
 
 extern "C" int bpe_encode_stats(bpe_handle *h, uint64_t *out /* [8] */) {
     if (!h || !out) return BPE_ERR_ARG;
-    memset(out, 0, 8 * sizeof(uint64_t));
+    memset(out, 0, 10 * sizeof(uint64_t));
     if (!h->enc) return BPE_OK;
     EncState *S = h->enc;
     EncCtl hc;
@@ -409,6 +441,7 @@ extern "C" int bpe_encode_stats(bpe_handle *h, uint64_t *out /* [8] */) {
     CU(cudaMemcpy(&hc, S->ctl, sizeof(EncCtl), cudaMemcpyDeviceToHost));
     out[0] = hc.memo_used; out[1] = hc.pool_used; out[2] = S->st_chunks_new; out[3] = S->st_direct; out[4] = S->st_long;
     out[5] = S->st_pieces; out[6] = S->st_fallbacks; out[7] = (uint64_t)(S->st_kernel_ms * 1000.0);
+    out[8] = S->st_retries; out[9] = S->st_tmp_ids;
     return BPE_OK;
 }
 

@@ -45,15 +45,19 @@ struct __align__(16) MemoSlot {           // 64 bytes
     u32 pad[4];
 };
 
+#define E2_OFF_TMP 0x80000000u   // PosSlot.off / e2_resolve: the ids are in the per-piece area
 struct __align__(16) PosSlot { u64 key; u32 ntok; u32 off; };   // key = chunk position + 1, 0 = empty
 
+#define E2_FAIL_OTHER 1u                  // pool / lists full, an oversize chunk, a chunk nobody could resolve: general path
+#define E2_FAIL_TMP 2u                    // the per-piece id area is too small: the host grows it and repeats the piece
 struct EncCtl {
     ull memo_used;       // claimed memo slots
-    ull pool_used;       // ids in the pool
+    ull pool_used;       // ids in the pool (encodings of memoised chunks: they live as long as the memo)
     u32 n_new;           // entries of the new-slot list
-    u32 fail;            // 1: something did not fit (pool, lists, an oversize chunk): the host takes the general path
+    u32 fail;            // E2_FAIL_* bits
     ull n_direct;        // entries of the direct list
     ull n_long;          // ... of which longer than E2_LMAX bytes
+    ull tmp_used;        // ids in the per-piece area (encodings of the direct chunks of THIS piece)
 };
 
 struct Enc2 {
@@ -62,11 +66,16 @@ struct Enc2 {
     u64 n;
     MemoSlot *memo; u64 memo_mask; u64 memo_limit;
     u32 *pool; u64 pool_cap;
+    u32 *tmp; u64 tmp_cap;           // per-piece id area; an offset with E2_OFF_TMP set points into it
     u32 *new_list; u32 new_cap;
     u64 *direct_list; u64 direct_cap;
     PosSlot *posmap; u64 pos_mask;
     EncCtl *ctl;
 };
+
+__device__ __forceinline__ u32 e2_id_at(const Enc2 &E, u32 off, u32 j) {
+    return (off & E2_OFF_TMP) ? E.tmp[(off & ~E2_OFF_TMP) + j] : __ldg(&E.pool[off + j]);
+}
 
 // ---- a tile of text + chunk-start bits in shared memory -----------------------------------------------------
 struct E2Tile {
@@ -153,7 +162,7 @@ __device__ __forceinline__ u64 e2_key(const E2Tile &T, u32 p, u32 len, u32 (&kw)
 __device__ __forceinline__ void e2_direct_append(const Enc2 &E, u64 pos, bool is_long) {
     const ull k = atomicAdd(&E.ctl->n_direct, 1ull);
     if (k < E.direct_cap) E.direct_list[k] = pos | (is_long ? (1ull << 63) : 0ull);
-    else E.ctl->fail = 1;
+    else atomicOr(&E.ctl->fail, E2_FAIL_OTHER);
     if (is_long) atomicAdd(&E.ctl->n_long, 1ull);
 }
 
@@ -191,7 +200,7 @@ __global__ void __launch_bounds__(E2_THREADS) k_enc_insert(Enc2 E) {
                     for (int j = 0; j < 8; ++j) m->key[j] = kw[j];
                     atomicAdd(&E.ctl->memo_used, 1ull);
                     const u32 q = atomicAdd(&E.ctl->n_new, 1u);
-                    if (q < E.new_cap) E.new_list[q] = (u32)slot; else E.ctl->fail = 1;
+                    if (q < E.new_cap) E.new_list[q] = (u32)slot; else atomicOr(&E.ctl->fail, E2_FAIL_OTHER);
                     placed = true;
                     break;
                 }
@@ -224,7 +233,7 @@ __global__ void k_enc_seed_specials(Enc2 E, const unsigned char *__restrict__ bl
         if (old == 0) {
             MemoSlot *m = &E.memo[slot];
             const ull o = atomicAdd(&E.ctl->pool_used, 1ull);
-            if (o >= E.pool_cap) { E.ctl->fail = 1; return; }
+            if (o >= E.pool_cap) { atomicOr(&E.ctl->fail, E2_FAIL_OTHER); return; }
             E.pool[o] = (u32)ids[s];
             m->off = (u32)o;
 #pragma unroll
@@ -235,7 +244,7 @@ __global__ void k_enc_seed_specials(Enc2 E, const unsigned char *__restrict__ bl
         }
         slot = (slot + 1) & E.memo_mask;
     }
-    E.ctl->fail = 1;
+    atomicOr(&E.ctl->fail, E2_FAIL_OTHER);
 }
 
 // regex.py:92-109 on a short token list held by one thread.  tok[] in/out, returns the new length.
@@ -272,7 +281,7 @@ __global__ void __launch_bounds__(128) k_enc_distinct(Enc2 E, RankTable rt, cons
     }
     const u32 len = e2_encode_short(tok, len0, rt);
     const ull off = atomicAdd(&E.ctl->pool_used, (ull)len);
-    if (off + len > E.pool_cap) { E.ctl->fail = 1; return; }
+    if (off + len > E.pool_cap) { atomicOr(&E.ctl->fail, E2_FAIL_OTHER); return; }
     for (u32 k = 0; k < len; ++k) E.pool[off + k] = tok[k];
     m->off = (u32)off;
     __threadfence();
@@ -305,10 +314,10 @@ __global__ void __launch_bounds__(128) k_enc_direct_short(Enc2 E, RankTable rt, 
         tok[len0++] = perm ? perm[b] : b;
     }
     const u32 len = e2_encode_short(tok, len0, rt);
-    const ull off = atomicAdd(&E.ctl->pool_used, (ull)len);
-    if (off + len > E.pool_cap) { E.ctl->fail = 1; return; }
-    for (u32 k = 0; k < len; ++k) E.pool[off + k] = tok[k];
-    e2_pos_insert(E, pos, len, (u32)off);
+    const ull off = atomicAdd(&E.ctl->tmp_used, (ull)len);
+    if (off + len > E.tmp_cap) { atomicOr(&E.ctl->fail, E2_FAIL_TMP); return; }
+    for (u32 k = 0; k < len; ++k) E.tmp[off + k] = tok[k];
+    e2_pos_insert(E, pos, len, (u32)off | E2_OFF_TMP);
 }
 
 // ---- pass 3b: listed LONG chunks: one CTA each, tokens in shared memory (as k_encode_long) --------------------
@@ -337,7 +346,7 @@ __global__ void __launch_bounds__(256) k_enc_direct_long(Enc2 E, RankTable rt, c
         }
         __syncthreads();
         const u32 len0 = s_len0;
-        if (len0 > ENC_LONG_MAX) { if (tid == 0) E.ctl->fail = 1; __syncthreads(); continue; }   // host: general path
+        if (len0 > ENC_LONG_MAX) { if (tid == 0) atomicOr(&E.ctl->fail, E2_FAIL_OTHER); __syncthreads(); continue; }   // host: general path
         for (u32 i = tid; i < len0; i += 256) { const u32 b = E.text[pos + i]; tk[i] = perm ? perm[b] : b; }
         u32 len = len0;
         __syncthreads();
@@ -397,13 +406,13 @@ __global__ void __launch_bounds__(256) k_enc_direct_long(Enc2 E, RankTable rt, c
             __syncthreads();
         }
         __syncthreads();
-        if (tid == 0) s_off = atomicAdd(&E.ctl->pool_used, (ull)len);
+        if (tid == 0) s_off = atomicAdd(&E.ctl->tmp_used, (ull)len);
         __syncthreads();
         const ull off = s_off;
-        if (off + len > E.pool_cap) { if (tid == 0) E.ctl->fail = 1; }
+        if (off + len > E.tmp_cap) { if (tid == 0) atomicOr(&E.ctl->fail, E2_FAIL_TMP); }
         else {
-            for (u32 i = tid; i < len; i += 256) E.pool[off + i] = tk[i];
-            if (tid == 0) e2_pos_insert(E, pos, len, (u32)off);
+            for (u32 i = tid; i < len; i += 256) E.tmp[off + i] = tk[i];
+            if (tid == 0) e2_pos_insert(E, pos, len, (u32)off | E2_OFF_TMP);
         }
         __syncthreads();
     }
@@ -464,7 +473,7 @@ __global__ void __launch_bounds__(E2_THREADS) k_enc_count(Enc2 E, u32 *__restric
         const u32 p = base + k;
         if (lo + p >= E.n) break;
         u32 nt = 0, off = 0;
-        if (e2_resolve(E, T, lo, p, nt, off)) sum += nt; else E.ctl->fail = 1;
+        if (e2_resolve(E, T, lo, p, nt, off)) sum += nt; else atomicOr(&E.ctl->fail, E2_FAIL_OTHER);
     }
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
@@ -518,7 +527,7 @@ __global__ void __launch_bounds__(E2_THREADS) k_enc_write(Enc2 E, const u64 *__r
     for (u32 c = 0; c < cnt; ++c) {
         const u32 nt = nts[c], off = offs[c];
         for (u32 j = 0; j < nt; ++j) {
-            const u32 v = __ldg(&E.pool[off + j]);
+            const u32 v = e2_id_at(E, off, j);
             if (dst + j < E2_OUT) s_out[dst + j] = v; else o[dst + j] = (int)v;
         }
         dst += nt;

@@ -247,9 +247,10 @@ class Engine:
         return out[: n.value]
 
     def encode_stats(self):
-        a = np.zeros(8, dtype=np.uint64)
+        a = np.zeros(10, dtype=np.uint64)
         self._check(self._lib.bpe_encode_stats(self._h, _ptr(a)), "bpe_encode_stats")
-        names = ("memo_chunks", "pool_ids", "new_chunks", "direct_chunks", "long_chunks", "pieces", "fallback_pieces", "kernel_us")
+        names = ("memo_chunks", "pool_ids", "new_chunks", "direct_chunks", "long_chunks", "pieces", "fallback_pieces", "kernel_us",
+                 "repeated_pieces", "direct_ids")
         return {k: int(v) for k, v in zip(names, a)}
 
     # ---- measurement / options ----

@@ -65,6 +65,7 @@ def test_memo_is_warm_and_follows_the_merges(eng, trained):
     n2 = eng.encode_stats()
     assert np.array_equal(a, w) and np.array_equal(b, w)
     assert n2["new_chunks"] == 0 and n2["memo_chunks"] == n1["memo_chunks"]
+    assert n2["pool_ids"] == n1["pool_ids"]                  # repeated calls do not grow the persistent state
     # fewer merges -> different ids: the table must not serve entries of the old merges
     m2 = merges[:100]
     assert np.array_equal(eng.encode_text_gpt4(data.tobytes(), m2), oracle.c_encode(data, offs, m2))
@@ -87,6 +88,9 @@ def test_tiny_memo_table_overflows_to_the_direct_path(eng, trained):
         st = eng.encode_stats()
         assert np.array_equal(got, w)
         assert st["direct_chunks"] > 10000 and st["memo_chunks"] <= 64   # the fill limit is checked without a lock: approximate
+        # the ids of directly encoded chunks live in a per-piece area (not in the memo's pool): it started too small for a
+        # text that is all direct chunks, was grown, and the piece was done again
+        assert st["repeated_pieces"] == 1 and st["direct_ids"] > 10000 and st["fallback_pieces"] == 0
         eng.set_option(E.OPT_SPLIT_PIECE, 1 << 16)         # several pieces per call share the (tiny) table
         assert np.array_equal(eng.encode_text_gpt4(data.tobytes(), merges), w)
         assert eng.encode_stats()["pieces"] > 5
