@@ -136,13 +136,13 @@ int bpe_encode_text_gpt4(bpe_handle *h, const uint8_t *bytes, uint64_t n, const 
  * encode_ordinary(part) for every part in between.  Here the occurrences are found on the device, become boundaries
  * of the GPT-4 split (the text on either side is split on its own) and single-id entries of the encode memo.
  * special_bytes: the specials' utf-8 bytes back to back, in dict order; special_offsets[n_special + 1]; at most 64
- * specials of 1..32 bytes each (BPE_ERR_ARG otherwise: the caller keeps the host split for those). */
+ * specials of 1..48 bytes each (BPE_ERR_ARG otherwise: the caller keeps the host split for those). */
 int bpe_encode_text_gpt4_special(bpe_handle *h, const uint8_t *bytes, uint64_t n, const int32_t *merges, int32_t n_merges,
                                  const uint8_t *byte_perm, const uint8_t *special_bytes, const uint32_t *special_offsets,
                                  const int32_t *special_ids, int32_t n_special, int32_t *out_ids, uint64_t out_cap,
                                  uint64_t *out_n);
 /* Counters of the memoised encode: out[0] distinct chunks in the memo table, [1] ids in its pool; of the last call:
- * [2] chunks newly added, [3] chunks encoded directly (no room in the table, or longer than 32 bytes), [4] of which
+ * [2] chunks newly added, [3] chunks encoded directly (no room in the table, or longer than 48 bytes), [4] of which
  * long, [5] pieces, [6] pieces that took the general path, [7] device microseconds of the encode kernels
  * (BPE_OPT_KERNEL_TIMING), [8] pieces done twice because the per-piece id area had to grow, [9] ids of the directly
  * encoded chunks of the last piece. */

@@ -31,7 +31,8 @@
 #define E2_THREADS 256
 #define E2_ITEMS 8
 #define E2_TILE (E2_THREADS * E2_ITEMS)   // 2048 text bytes per CTA
-#define E2_LMAX 32                        // chunks of up to 32 bytes are memoised (and encoded by one thread)
+#define E2_LMAX 48                        // chunks of up to 48 bytes are memoised (and encoded by one thread): key + header = one 64-byte slot
+#define E2_KW (E2_LMAX / 4)               // key words
 #define E2_PROBES 24
 #define E2_HALO 64                        // bytes after the tile that its chunks may reach into (>= E2_LMAX + 4, multiple of 32)
 #define E2_OUT (E2_TILE + E2_LMAX)           // ids of one tile staged in shared memory by k_enc_write
@@ -41,9 +42,9 @@ struct __align__(16) MemoSlot {           // 64 bytes
     u64 tag;                              // 0 = empty, else (hash | 1)
     u32 meta;                             // len (bits 0..7) | ntok (bits 8..15; E2_PENDING = not encoded yet)
     u32 off;                              // first id in the pool
-    u32 key[8];                           // the chunk's bytes, zero padded
-    u32 pad[4];
+    u32 key[E2_KW];                       // the chunk's bytes, zero padded
 };
+static_assert(sizeof(MemoSlot) == 64 && E2_LMAX % 16 == 0, "one slot = header + key = 64 bytes, key compared as 16-byte vectors");
 
 #define E2_OFF_TMP 0x80000000u   // PosSlot.off / e2_resolve: the ids are in the per-piece area
 struct __align__(16) PosSlot { u64 key; u32 ntok; u32 off; };   // key = chunk position + 1, 0 = empty
@@ -124,30 +125,33 @@ __device__ __forceinline__ void e2_load_tile(const Enc2 &E, u64 lo, E2Tile T) {
 __device__ __forceinline__ u32 e2_chunk_len(const E2Tile &T, u32 p) {
     const u32 q = p + 1;
     const u32 wi = q >> 5, sh = q & 31u;
-    u64 two = (u64)T.s_bits[wi] | ((u64)T.s_bits[wi + 1] << 32);
-    two >>= sh;
-    const u32 len = two ? (u32)__ffsll((long long)two) : 65u;
+    const u64 two = ((u64)T.s_bits[wi] | ((u64)T.s_bits[wi + 1] << 32)) >> sh;     // start bits of bytes q .. q + 63 - sh
+    u32 len;
+    if (two) len = (u32)__ffsll((long long)two);
+    else {                                                                          // ... and of the word after them
+        const u32 third = T.s_bits[wi + 2];
+        len = third ? (64u - sh) + (u32)__ffs(third) : E2_LMAX + 1;
+    }
     return len > E2_LMAX ? E2_LMAX + 1 : len;
 }
 
 // 64-bit tag of a chunk from its zero-padded key words (never 0: bit 0 is set)
-__device__ __forceinline__ u64 e2_tag(const u32 (&kw)[8], u32 len) {
+__device__ __forceinline__ u64 e2_tag(const u32 (&kw)[E2_KW], u32 len) {
     u64 h = 0x9e3779b97f4a7c15ull ^ ((u64)len << 56);
     h = hash64(h ^ ((u64)kw[0] | ((u64)kw[1] << 32)));
-    if (len > 8) {
-        h = hash64(h ^ ((u64)kw[2] | ((u64)kw[3] << 32)));
-        if (len > 16) { h = hash64(h ^ ((u64)kw[4] | ((u64)kw[5] << 32))); h = hash64(h ^ ((u64)kw[6] | ((u64)kw[7] << 32))); }
-    }
+#pragma unroll
+    for (u32 j = 2; j < E2_KW; j += 2)
+        if (len > 4 * j) h = hash64(h ^ ((u64)kw[j] | ((u64)kw[j + 1] << 32)));
     return h | 1ull;
 }
 
 // key words of the chunk [p, p+len) of the tile (len <= E2_LMAX): zero padded; returns the tag
-__device__ __forceinline__ u64 e2_key(const E2Tile &T, u32 p, u32 len, u32 (&kw)[8]) {
+__device__ __forceinline__ u64 e2_key(const E2Tile &T, u32 p, u32 len, u32 (&kw)[E2_KW]) {
     const u32 *s32 = reinterpret_cast<const u32 *>(T.s_b);
     const u32 w0 = p >> 2, sh = (p & 3u) * 8u;
     const u32 nw = (len + 3u) >> 2;
 #pragma unroll
-    for (u32 j = 0; j < 8; ++j) {
+    for (u32 j = 0; j < E2_KW; ++j) {
         u32 v = 0;
         if (j < nw) {
             v = __funnelshift_r(s32[w0 + j], s32[w0 + j + 1], sh);
@@ -183,7 +187,7 @@ __global__ void __launch_bounds__(E2_THREADS) k_enc_insert(Enc2 E) {
         if (lo + p >= E.n) break;
         const u32 len = e2_chunk_len(T, p);
         if (len > E2_LMAX) { e2_direct_append(E, lo + p, true); continue; }
-        u32 kw[8];
+        u32 kw[E2_KW];
         const u64 tag = e2_key(T, p, len, kw);
         u64 slot = (tag >> 1) & E.memo_mask;
         bool placed = false;
@@ -197,7 +201,7 @@ __global__ void __launch_bounds__(E2_THREADS) k_enc_insert(Enc2 E) {
                     MemoSlot *m = &E.memo[slot];
                     m->meta = len | (E2_PENDING << 8);
 #pragma unroll
-                    for (int j = 0; j < 8; ++j) m->key[j] = kw[j];
+                    for (int j = 0; j < E2_KW; ++j) m->key[j] = kw[j];
                     atomicAdd(&E.ctl->memo_used, 1ull);
                     const u32 q = atomicAdd(&E.ctl->n_new, 1u);
                     if (q < E.new_cap) E.new_list[q] = (u32)slot; else atomicOr(&E.ctl->fail, E2_FAIL_OTHER);
@@ -219,9 +223,9 @@ __global__ void k_enc_seed_specials(Enc2 E, const unsigned char *__restrict__ bl
     const int s = blockIdx.x * blockDim.x + threadIdx.x;
     if (s >= k) return;
     const u32 lo = off[s], len = off[s + 1] - lo;      // 1 .. E2_LMAX (checked by the host)
-    u32 kw[8];
+    u32 kw[E2_KW];
 #pragma unroll
-    for (u32 j = 0; j < 8; ++j) {
+    for (u32 j = 0; j < E2_KW; ++j) {
         u32 v = 0;
         for (u32 t = 0; t < 4; ++t) if (4 * j + t < len) v |= (u32)blob[lo + 4 * j + t] << (8 * t);
         kw[j] = v;
@@ -237,7 +241,7 @@ __global__ void k_enc_seed_specials(Enc2 E, const unsigned char *__restrict__ bl
             E.pool[o] = (u32)ids[s];
             m->off = (u32)o;
 #pragma unroll
-            for (int j = 0; j < 8; ++j) m->key[j] = kw[j];
+            for (int j = 0; j < E2_KW; ++j) m->key[j] = kw[j];
             m->meta = len | (1u << 8);
             atomicAdd(&E.ctl->memo_used, 1ull);
             return;
@@ -422,7 +426,7 @@ __global__ void __launch_bounds__(256) k_enc_direct_long(Enc2 E, RankTable rt, c
 __device__ __forceinline__ bool e2_resolve(const Enc2 &E, const E2Tile &T, u64 lo, u32 p, u32 &ntok, u32 &off) {
     const u32 len = e2_chunk_len(T, p);
     if (len <= E2_LMAX) {
-        u32 kw[8];
+        u32 kw[E2_KW];
         const u64 tag = e2_key(T, p, len, kw);
         u64 slot = (tag >> 1) & E.memo_mask;
 #pragma unroll 1
@@ -432,9 +436,12 @@ __device__ __forceinline__ bool e2_resolve(const Enc2 &E, const E2Tile &T, u64 l
             const u64 t = (u64)head.x | ((u64)head.y << 32);
             if (t == 0) break;
             if (t == tag) {
-                const uint4 k0 = *reinterpret_cast<const uint4 *>(m->key), k1 = *reinterpret_cast<const uint4 *>(m->key + 4);
-                const bool same = (head.z & 0xffu) == len && k0.x == kw[0] && k0.y == kw[1] && k0.z == kw[2] && k0.w == kw[3] &&
-                                  k1.x == kw[4] && k1.y == kw[5] && k1.z == kw[6] && k1.w == kw[7];
+                bool same = (head.z & 0xffu) == len;
+#pragma unroll
+                for (int v = 0; v < E2_KW / 4; ++v) {                           // the key, 16 bytes at a time
+                    const uint4 k = *reinterpret_cast<const uint4 *>(m->key + 4 * v);
+                    same = same && k.x == kw[4 * v] && k.y == kw[4 * v + 1] && k.z == kw[4 * v + 2] && k.w == kw[4 * v + 3];
+                }
                 const u32 nt = (head.z >> 8) & 0xffu;
                 if (same && nt != E2_PENDING) { ntok = nt; off = head.w; return true; }
                 break;   // a different chunk with the same tag (or a slot that could not be encoded): position map

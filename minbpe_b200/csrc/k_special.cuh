@@ -15,7 +15,7 @@
 #include "split_logic.h"
 
 #define SPEC_MAX 64          // specials per call (bit mask per first byte)
-#define SPEC_MAX_LEN 32      // bytes per special = E2_LMAX: a special must fit one memo slot
+#define SPEC_MAX_LEN 48      // bytes per special = E2_LMAX (k_encode2.cuh): a special must fit one memo slot
 
 struct SpecDev {
     const unsigned char *blob;   // the specials' bytes back to back

@@ -35,7 +35,7 @@ static int spec_set(bpe_handle *h, const uint8_t *bytes, const uint32_t *offsets
     if (k > SPEC_MAX) return fail(h, BPE_ERR_ARG, "more than 64 special tokens in one call");
     for (int s = 0; s < k; ++s) {
         if (offsets[s + 1] <= offsets[s]) return fail(h, BPE_ERR_ARG, "special tokens must not be empty");
-        if (offsets[s + 1] - offsets[s] > SPEC_MAX_LEN) return fail(h, BPE_ERR_ARG, "special tokens longer than 32 bytes are not handled on the device");
+        if (offsets[s + 1] - offsets[s] > SPEC_MAX_LEN) return fail(h, BPE_ERR_ARG, "special tokens longer than 48 bytes are not handled on the device");
         if (ids[s] < 0) return fail(h, BPE_ERR_ARG, "special-token ids must be >= 0");
     }
     if (!h->spec) h->spec = new (std::nothrow) SpecSet();

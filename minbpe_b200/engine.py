@@ -220,7 +220,7 @@ class Engine:
             return out[: n.value].tobytes(), -1
         raise EngineError("bpe_decode: capacity retry failed")
 
-    SPECIAL_MAX, SPECIAL_MAX_BYTES = 64, 32      # limits of bpe_encode_text_gpt4_special
+    SPECIAL_MAX, SPECIAL_MAX_BYTES = 64, 48      # limits of bpe_encode_text_gpt4_special
 
     def encode_text_gpt4(self, data, merges, byte_perm=None, out=None, specials=None):
         """-> ids int32 of utf-8 `data`: GPT-4 split + encode, both on the GPU (regex.py:111-121).

@@ -328,7 +328,7 @@ class RegexTokenizer(Tokenizer):
         return True
 
     def _device_specials(self, special):
-        """The device front end takes at most 64 specials of 1..32 utf-8 bytes and non-negative int32 ids; anything else
+        """The device front end takes at most 64 specials of 1..48 utf-8 bytes and non-negative int32 ids; anything else
         keeps the reference's host split (below)."""
         E = Engine
         return (0 < len(special) <= E.SPECIAL_MAX and

@@ -1,7 +1,7 @@
 #!/usr/bin/env python3
 """TEST INFRASTRUCTURE (BPE_LIB_PATH = the emulator build): random small inputs through both encode entry points
 (bpe_encode with host offsets, bpe_encode_text_gpt4) against oracle.c_encode — sizes around the kernels' tile (2048 B),
-halo (64 B), memo limit (32 B) and long-chunk (64 / 8192 tokens) boundaries, tiny memo tables, several pieces per call.
+halo (64 B), memo limit (48 B) and long-chunk (8192 tokens) boundaries, tiny memo tables, several pieces per call.
 Allocations sit in front of guard pages, so an out-of-bounds access of a kernel ends the process."""
 import os
 import sys
@@ -24,7 +24,7 @@ def random_text(rng, n_words, max_word):
     for _ in range(n_words):
         k = int(rng.integers(1, max_word + 1))
         if rng.random() < 0.02:
-            k = int(rng.choice([31, 32, 33, 34, 63, 64, 65, 66, 100, 2040, 2048, 2056, 8190, 8192]))
+            k = int(rng.choice([31, 32, 33, 34, 46, 47, 48, 49, 50, 63, 64, 65, 66, 100, 2040, 2048, 2056, 8190, 8192]))
             words.append("".join(rng.choice(list("abc"), size=k)))
         else:
             words.append("".join(rng.choice(alphabet, size=k)))

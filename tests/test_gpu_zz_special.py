@@ -42,11 +42,11 @@ def tok():
 
 def test_encode_with_specials_through_the_class(tok):
     a, b, c = tok.text[:100000], tok.text[100000:200000], tok.text[200000:300000]
-    sp = {"<|endoftext|>": 100257, "<|fim_prefix|>": 100258, "<|x|>": 100259, " <sp> ": 100260}
+    sp = {"<|endoftext|>": 100257, "<|fim_prefix|>": 100258, "<|x|>": 100259, " <sp> ": 100260, "<|" + "z" * 44 + "|>": 100261}
     tok.register_special_tokens(sp)
     cases = [a + "<|endoftext|>" + b + "<|fim_prefix|><|x|>" + c,
              "<|endoftext|>" + a + "  <|endoftext|>\n\n" + b + " <sp> 'll" + c[:70000] + "<|x|>",
-             a + " <|x|> 123<|x|>456 <|x|>'s " + b]
+             a + " <|x|> 123<|x|>456 <|x|>'s " + b + "<|" + "z" * 44 + "|>" + c[:1000]]
     for t in cases:
         assert tok.encode(t, allowed_special="all") == ref_encode(t, sp, tok.m)
         sub = {"<|x|>"}
@@ -54,11 +54,11 @@ def test_encode_with_specials_through_the_class(tok):
         assert tok.encode(t, allowed_special="none") == ref_encode(t, {"\x00never": 0}, tok.m)      # specials as ordinary text
     with pytest.raises(AssertionError):
         tok.encode(cases[0])                                                                         # none_raise (regex.py:139)
-    # a special the device does not take (longer than 32 bytes) keeps the host split: same answer
+    # a special the device does not take (longer than 48 bytes) keeps the host split: same answer
     long_sp = dict(sp)
-    long_sp["<|" + "y" * 40 + "|>"] = 100300
+    long_sp["<|" + "y" * 60 + "|>"] = 100300
     tok.register_special_tokens(long_sp)
-    t = cases[0] + "<|" + "y" * 40 + "|>" + a[:70000]
+    t = cases[0] + "<|" + "y" * 60 + "|>" + a[:70000]
     assert tok.encode(t, allowed_special="all") == ref_encode(t, long_sp, tok.m)
     ids = tok.encode(cases[0], allowed_special="all")
     assert tok.decode(ids) == cases[0]
@@ -122,7 +122,7 @@ def test_pieces_and_oversize_chunks_with_specials(tok):
     assert eng.encode_text_gpt4(text.encode("utf-8"), tok.m, specials=spec).tolist() == want     # and the memo works again
     # limits of the device front end are errors of the C ABI (the class keeps the host split for such sets)
     with pytest.raises(E.EngineError):
-        eng.encode_text_gpt4(b"abc", tok.m, specials=[(b"x" * 33, 1)])
+        eng.encode_text_gpt4(b"abc", tok.m, specials=[(b"x" * 49, 1)])
     with pytest.raises(E.EngineError):
         eng.encode_text_gpt4(b"abc", tok.m, specials=[(b"", 1)])
     eng.close()
