@@ -242,6 +242,9 @@ typedef struct {
     uint64_t table_used;     /* occupied slots */
     uint64_t h2d_bytes;      /* host->device bytes copied by the last load/encode call */
     uint64_t d2h_bytes;      /* device->host bytes copied by the last train/encode/read call */
+    uint64_t hist_kernel;    /* byte-pair histogram kernel of the last bpe_train / bpe_step_begin on a byte stream:
+                                1 = k_hist_dense_packed, 2 = k_hist_dense (the first use of a handle runs both and keeps
+                                the packed one only if all 65,536 counters agree), 0 = none run yet */
 } bpe_timing;
 int bpe_get_timing(bpe_handle *h, bpe_timing *out);
 

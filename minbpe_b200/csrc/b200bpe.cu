@@ -55,6 +55,8 @@ struct bpe_handle {
     u32 delta_cap = 0;                 // vocabulary capacity of the OWNED buffer `delta` (step mode uses the caller's)
     u32 max_id = 255;                  // largest id in the loaded stream (bpe_load_ids); byte streams: 255
     ull *dense = nullptr;
+    ull *dense2 = nullptr; u32 *d_cmp = nullptr;   // first-use cross-check of the packed histogram kernel (hist_dense)
+    int hist_mode = 0;                             // 0 = not decided, 1 = k_hist_dense_packed, 2 = k_hist_dense
     u32 *d_err = nullptr;
     int *log_pairs = nullptr; long long *log_counts = nullptr; int log_cap = 0;
     Best *partials = nullptr;
@@ -197,6 +199,8 @@ extern "C" int bpe_destroy(bpe_handle *h) {
     if (h->seg_offs) cudaFree(h->seg_offs);
     if (h->delta) cudaFree(h->delta);
     if (h->dense) cudaFree(h->dense);
+    if (h->dense2) cudaFree(h->dense2);
+    if (h->d_cmp) cudaFree(h->d_cmp);
     if (h->d_err) cudaFree(h->d_err);
     if (h->log_pairs) cudaFree(h->log_pairs);
     if (h->log_counts) cudaFree(h->log_counts);
@@ -574,6 +578,43 @@ static int ensure_delta(bpe_handle *h, u32 V) {
     return BPE_OK;
 }
 
+// Byte-pair histogram of the current (byte) stream into dense_out[65536] (zeroed by the caller).
+// k_hist_dense_packed (dense 16-bit counters in 128 KB of shared memory) replaces k_hist_dense (hashed per-block table +
+// __match_any_sync folding, 19 ms per GiB).  It was written when no GPU was reachable and has only run on the CPU SIMT
+// emulator, so a handle's FIRST histogram runs both kernels and compares all 65,536 counters on the device: equal -> the
+// packed kernel from then on; different (or 128 KB of shared memory refused) -> k_hist_dense stays.  bpe_timing.hist_kernel
+// reports which one is in use.  (Drop the cross-check once `pytest -m gpu` has passed on a B200 with hist_kernel == 1.)
+static int hist_dense(bpe_handle *h, ull *dense_out) {
+    const int grid_old = h->sms * 3;
+    if (h->hist_mode == 0) {
+        h->hist_mode = 2;
+        if (cudaFuncSetAttribute(k_hist_dense_packed, cudaFuncAttributeMaxDynamicSharedMemorySize, HP_SMEM_BYTES) == cudaSuccess) {
+            if (!h->dense2) CU(cudaMalloc(&h->dense2, 65536 * 8));
+            if (!h->d_cmp) CU(cudaMalloc(&h->d_cmp, 4));
+            CU(cudaMemsetAsync(h->dense2, 0, 65536 * 8, h->stream));
+            CU(cudaMemsetAsync(h->d_cmp, 0, 4, h->stream));
+            k_hist_dense<<<grid_old, 256, 0, h->stream>>>(h->buf[0], h->buf[1], h->ctl, h->edge[0], h->edge[1], dense_out, h->d_err);
+            k_hist_dense_packed<<<h->sms, HP_THREADS, HP_SMEM_BYTES, h->stream>>>(h->buf[0], h->buf[1], h->ctl, h->edge[0], h->edge[1], h->dense2, h->d_err);
+            k_dense_compare<<<65536 / 256, 256, 0, h->stream>>>(dense_out, h->dense2, h->d_cmp);
+            h->tm.kernel_launches += 3;
+            u32 differ = 1;
+            cudaError_t e = cudaMemcpyAsync(&differ, h->d_cmp, 4, cudaMemcpyDeviceToHost, h->stream);
+            if (e == cudaSuccess) e = cudaStreamSynchronize(h->stream);
+            if (e != cudaSuccess) return fail(h, BPE_ERR_CUDA, std::string("hist_dense: ") + cudaGetErrorString(e));
+            if (!differ) h->hist_mode = 1;
+            h->tm.hist_kernel = (uint64_t)h->hist_mode;
+            return BPE_OK;      // dense_out holds k_hist_dense's result either way
+        }
+    }
+    if (h->hist_mode == 1)
+        k_hist_dense_packed<<<h->sms, HP_THREADS, HP_SMEM_BYTES, h->stream>>>(h->buf[0], h->buf[1], h->ctl, h->edge[0], h->edge[1], dense_out, h->d_err);
+    else
+        k_hist_dense<<<grid_old, 256, 0, h->stream>>>(h->buf[0], h->buf[1], h->ctl, h->edge[0], h->edge[1], dense_out, h->d_err);
+    h->tm.kernel_launches += 1;
+    h->tm.hist_kernel = (uint64_t)h->hist_mode;
+    return BPE_OK;
+}
+
 // (re)build the pair-count table from the current stream
 static int build_table(bpe_handle *h, u64 cap) {
     int rc;
@@ -589,9 +630,9 @@ static int build_table(bpe_handle *h, u64 cap) {
     if (h->bytes_only) {
         CU(cudaMemsetAsync(h->dense, 0, 65536 * 8, h->stream));
         CU(cudaMemsetAsync(h->d_err, 0, 4, h->stream));
-        k_hist_dense<<<h->sms * 3, 256, 0, h->stream>>>(h->buf[0], h->buf[1], h->ctl, h->edge[0], h->edge[1], h->dense, h->d_err);
+        if ((rc = hist_dense(h, h->dense))) return rc;
         k_dense_to_table<<<65536 / 256, 256, 0, h->stream>>>(h->dense, h->table, h->ctl);
-        h->tm.kernel_launches += 2;
+        h->tm.kernel_launches += 1;
     } else {
         k_hist_hash<<<h->sms * 8, 256, 0, h->stream>>>(h->buf[0], h->buf[1], h->ctl, h->edge[0], h->edge[1], h->table, 0);
         h->tm.kernel_launches += 1;

@@ -91,6 +91,70 @@ __global__ void __launch_bounds__(256) k_hist_dense(const u32 *__restrict__ buf0
         if (s_key[i] != 0xffffffffu && s_cnt[i]) atomicAdd(&dense[s_key[i]], (ull)s_cnt[i]);
 }
 
+// The same histogram with a DENSE per-CTA table: all 65,536 byte pairs as 16-bit counters packed two per word
+// (128 KB of dynamic shared memory, one CTA of 1024 threads per SM), one shared-memory atomicAdd per pair, no hashing and
+// no warp-level matching.  A counter cannot overflow: the CTA flushes its table into the global vector (and clears it)
+// after every round of at most HP_ROUND_TOKENS (< 65,536) tokens.  Rounds have the same trip count for every warp of the
+// CTA, so the flush barriers are uniform.
+#define HP_THREADS 1024
+#define HP_SEGS_PER_WARP 3                                  // segments of 512 tokens per warp per round
+#define HP_ROUND_TOKENS ((HP_THREADS / 32) * HP_SEGS_PER_WARP * SEG_TOKENS)
+#define HP_SMEM_BYTES (65536 * 2)
+static_assert(HP_ROUND_TOKENS < 65536, "a 16-bit counter must survive one round");
+__global__ void __launch_bounds__(HP_THREADS) k_hist_dense_packed(const u32 *__restrict__ buf0, const u32 *__restrict__ buf1,
+                                                                  const Ctl *__restrict__ ctl, const Edge *e0, const Edge *e1,
+                                                                  ull *__restrict__ dense, u32 *__restrict__ err) {
+    extern __shared__ u32 s_hist[];   // [32768]: bin i = bits 16*(i&1).. of word i>>1
+    const u32 tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, wpb = HP_THREADS / 32;
+    for (u32 i = tid; i < 32768u; i += HP_THREADS) s_hist[i] = 0;
+    __syncthreads();
+    const u32 *__restrict__ w = ctl->cur ? buf1 : buf0;
+    const Edge *e = edges_cur(ctl, e0, e1);
+    const u32 nseg = ctl->nseg;
+    // segment t belongs to CTA (t / wpb) % gridDim.x, warp t % wpb; this CTA's k-th segment group = blockIdx.x + k * gridDim.x
+    const u32 groups = (nseg + wpb - 1) / wpb;                                  // groups of wpb consecutive segments
+    const u32 my_groups = groups > blockIdx.x ? (groups - blockIdx.x + gridDim.x - 1) / gridDim.x : 0u;
+    const u32 rounds = (my_groups + HP_SEGS_PER_WARP - 1) / HP_SEGS_PER_WARP;   // block-uniform
+    for (u32 r = 0; r < rounds; ++r) {
+        for (u32 j = 0; j < HP_SEGS_PER_WARP; ++j) {
+            const u32 k = r * HP_SEGS_PER_WARP + j;
+            if (k >= my_groups) break;
+            const u32 t = (blockIdx.x + k * gridDim.x) * wpb + warp;
+            if (t >= nseg) continue;
+            const u32 count = e[t].count;
+            const u32 *__restrict__ seg = w + (u64)t * SEG_TOKENS;
+            for (u32 i0 = lane * 4; i0 < count; i0 += 128) {
+                const SegTokens q = seg_load4(seg, count, i0, e, t, nseg);
+#pragma unroll
+                for (int c = 0; c < 4; ++c) {
+                    const u32 left = q.t[c] & TOK_MASK, right = q.t[c + 1];
+                    if ((u32)c < q.nvalid && !(right & TOK_FLAG)) {
+                        if (left > 255u || right > 255u) *err = 1;
+                        const u32 bin = (left & 255u) << 8 | (right & 255u);
+                        atomicAdd(&s_hist[bin >> 1], 1u << (16u * (bin & 1u)));
+                    }
+                }
+            }
+        }
+        __syncthreads();
+        for (u32 i = tid; i < 32768u; i += HP_THREADS) {
+            const u32 v = s_hist[i];
+            if (v) {
+                if (v & 0xffffu) atomicAdd(&dense[2 * i], (ull)(v & 0xffffu));
+                if (v >> 16) atomicAdd(&dense[2 * i + 1], (ull)(v >> 16));
+                s_hist[i] = 0;
+            }
+        }
+        __syncthreads();
+    }
+}
+
+// first-use cross-check of the packed histogram against k_hist_dense (b200bpe.cu hist_dense): flag |= 1 on any difference
+__global__ void k_dense_compare(const ull *__restrict__ a, const ull *__restrict__ b, u32 *__restrict__ flag) {
+    const u32 i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < 65536u && a[i] != b[i]) *flag = 1;
+}
+
 // dense 256x256 vector -> table entries (one thread per bin)
 __global__ void k_dense_to_table(const ull *__restrict__ dense, Table t, Ctl *ctl) {
     const u32 i = blockIdx.x * blockDim.x + threadIdx.x;

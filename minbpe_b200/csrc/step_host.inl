@@ -27,13 +27,17 @@ extern "C" int bpe_step_begin(bpe_handle *h, uint64_t *dense_dev) {
     CU(cudaSetDevice(h->device));
     CU(cudaMemsetAsync(dense_dev, 0, 65536 * 8, h->stream));
     CU(cudaMemsetAsync(h->d_err, 0, 4, h->stream));
-    k_hist_dense<<<h->sms * 3, 256, 0, h->stream>>>(h->buf[0], h->buf[1], h->ctl, h->edge[0], h->edge[1], (ull *)dense_dev, h->d_err);
+    h->tm.kernel_launches = 0;
+    {
+        int rc0 = hist_dense(h, (ull *)dense_dev);
+        if (rc0) return rc0;
+    }
     // which pairs occur in THIS shard (before the caller sums the histogram across ranks)
     if (!h->d_present) CU(cudaMalloc(&h->d_present, (1u << PRESENT_LOG2) / 8));
     CU(cudaMemsetAsync(h->d_present, 0, (1u << PRESENT_LOG2) / 8, h->stream));
     k_present_init<<<65536 / 256, 256, 0, h->stream>>>((const ull *)dense_dev, h->d_present);
     CU(cudaGetLastError());
-    h->tm.kernel_launches = 2;
+    h->tm.kernel_launches += 1;
     return BPE_OK;
 }
 
