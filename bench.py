@@ -751,7 +751,8 @@ def run_sharded(args, rank, world, local):
 
     # ---- e2e: host buffers -> merges through the C ABI (device split + sharded loop), wall clock, max over ranks ----
     pinned = pin_host(raw)
-    eng.load_text_gpt4(raw)          # untimed warm-up of the load path
+    eng.load_text_gpt4(raw)          # untimed warm-up of the load path ...
+    ShardedTrainer(step, rank, world, poll_every=16, exchange=args.exchange).prepare(W + K)   # ... and of the first histogram / table build
     sync_all()
     t0 = time.perf_counter()
     eng.load_text_gpt4(raw)
