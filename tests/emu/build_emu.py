@@ -78,11 +78,17 @@ def build(force=False):
         with open(os.path.join(OUT, "src", name), "w") as fh:
             fh.write(text)
     opt = os.environ.get("EMU_OPT", "-O1")
-    cmd = ["g++", "-std=c++17", opt, "-g", "-fPIC", "-shared", "-fno-strict-aliasing", "-Wno-unknown-pragmas", "-Wno-attributes",
+    # EMU_SANITIZE=1: UBSan's alignment check turns every vector access of the kernels (uint2 / uint4 / ulonglong2 loads and
+    # stores carry their CUDA alignment here) into a trap when the address is not aligned as the GPU requires — x86 itself
+    # would not notice.  Load the result with LD_PRELOAD=$(g++ -print-file-name=libubsan.so) under python.
+    san = ["-fsanitize=alignment", "-fno-sanitize-recover=alignment"] if os.environ.get("EMU_SANITIZE") else []
+    cmd = ["g++", "-std=c++17", opt, "-g", "-fPIC", "-shared", "-fno-strict-aliasing", "-Wno-unknown-pragmas", "-Wno-attributes"] + san + [
            "-I", HERE, "-I", os.path.join(ROOT, "include"), "-I", os.path.join(OUT, "src"),
            os.path.join(OUT, "src", "b200bpe_emu.cpp"), os.path.join(HERE, "cuda_emu.cpp"), "-o", LIB, "-lpthread"]
+    if san:
+        cmd[cmd.index("-o") + 1] = LIB.replace(".so", "_ubsan.so")
     subprocess.check_call(cmd)
-    return LIB
+    return cmd[cmd.index("-o") + 1]
 
 
 if __name__ == "__main__":

@@ -22,7 +22,9 @@
 //   * several OS threads may launch at the same time (one per emulated GPU / rank): peer memory is plain host
 //     memory, release/acquire accesses map to C++ atomics;
 //   * cudaMalloc places every allocation in front of an inaccessible guard page (EMU_GUARD=0 turns it off) and
-//     fills it with 0xCD, so an overrun or a read of never-written memory shows.
+//     fills it with 0xCD, so an overrun or a read of never-written memory shows;
+//   * the vector types carry their CUDA alignment: a build with EMU_SANITIZE=1 (build_emu.py: UBSan alignment check) traps on
+//     every uint2 / uint4 / ulonglong2 access that a GPU would fault on.
 #pragma once
 #define BPE_SIMT_EMU 1
 #include <stdint.h>
