@@ -161,6 +161,12 @@ void spin() {
     if ((s->spins & 63u) == 0) { s->cur->state = F_SPIN; to_main(); }
 }
 
+static int order_mode() {
+    static int v = -1;
+    if (v < 0) { const char *e = getenv("EMU_ORDER"); v = !e ? 0 : (e[0] == 'r' && e[1] == 'e') ? 1 : (e[0] == 'r' && e[1] == 'a') ? 2 : 0; }
+    return v;
+}
+
 static void run_block(Sched *s, const LaunchCfg &cfg, dim3 bid) {
     const unsigned n = cfg.block.x * cfg.block.y * cfg.block.z;
     s->nthreads = n; s->alive = n; s->bar_gen = 1; s->bar_arrived = 0;
@@ -182,10 +188,24 @@ static void run_block(Sched *s, const LaunchCfg &cfg, dim3 bid) {
         for (int r = 0; r < 6; ++r) *--sp = nullptr;   // rbp rbx r12 r13 r14 r15
         f.sp = sp;
     }
+    // Order in which the runnable threads of the block get the processor.  CUDA promises none: a kernel whose result
+    // depends on it has a data race (a missing __syncthreads / __syncwarp).  EMU_ORDER=reverse | random (default: by
+    // thread index) lets the test-suite run under other interleavings.
+    static thread_local unsigned order[MAX_THREADS];
+    static thread_local unsigned long long rng = 0x9e3779b97f4a7c15ull;
+    const int mode = order_mode();
+    for (unsigned t = 0; t < n; ++t) order[t] = mode == 1 ? n - 1 - t : t;
     unsigned long long idle_rounds = 0;
     while (s->alive) {
         bool progress = false, spinning = false;
-        for (unsigned t = 0; t < n; ++t) {
+        if (mode == 2)
+            for (unsigned t = n - 1; t > 0; --t) {
+                rng ^= rng << 13; rng ^= rng >> 7; rng ^= rng << 17;
+                const unsigned j = (unsigned)(rng % (t + 1));
+                const unsigned x = order[t]; order[t] = order[j]; order[j] = x;
+            }
+        for (unsigned k = 0; k < n; ++k) {
+            const unsigned t = order[k];
             Fiber &f = s->fib[t];
             if (f.state == F_DONE) continue;
             if (f.state == F_WAIT_BAR && f.bar_gen == s->bar_gen) continue;

@@ -17,6 +17,8 @@
 //   * __syncthreads / warp collectives (__shfl*_sync, __ballot_sync, __all_sync, __reduce_*_sync) are rendezvous
 //     points: a fiber waits there until the other threads of the block / the other lanes named in the mask that are
 //     still alive have arrived — divergence, early exits and data-dependent loops between them behave as on a GPU;
+//   * the threads of a block run in thread-index order between two synchronisation points, or — EMU_ORDER=reverse | random —
+//     in another order: a kernel whose result depends on that order has a data race;
 //   * blocks of a grid run one after another in blockIdx order (legal: CUDA promises no inter-block progress);
 //     spin-waits on memory (`ld.volatile`, `ld.acquire.sys`) yield to the other fibers and give up after a bound;
 //   * several OS threads may launch at the same time (one per emulated GPU / rank): peer memory is plain host

@@ -32,11 +32,14 @@ def _env(lib):
     return env
 
 
-def _pytest(lib, files, k=None):
+def _pytest(lib, files, k=None, order=None):
     cmd = [sys.executable, "-m", "pytest", "-x", "-q", "-m", "gpu", "-p", "no:cacheprovider", "-o", "timeout=900"] + files
     if k:
         cmd += ["-k", k]
-    return subprocess.Popen(cmd, cwd=ROOT, env=_env(lib), stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
+    env = _env(lib)
+    if order:        # thread interleaving of the emulator (by index / reverse / random): a kernel that cares has a data race
+        env["EMU_ORDER"] = order
+    return subprocess.Popen(cmd, cwd=ROOT, env=env, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
 
 
 @pytest.fixture(scope="module")
@@ -49,11 +52,11 @@ def jobs():
         # round-2 kernels that have not run on a GPU yet — memoised chunk encode (k_encode2.cuh), bpe_replay / resume, the
         # special-token front end (k_special.cuh), file / shard entry points — and bpe_decode
         "new_kernels": _pytest(lib, [t("test_gpu_zy_encode2.py"), t("test_gpu_zz_resume.py"), t("test_gpu_zz_file.py"), t("test_gpu_zz_special.py"), t("test_gpu_zz_gpt2.py"), t("test_gpu_zz_gpt4.py"), t("test_gpu_zz_hist.py"),
-                                       t("test_gpu_decode.py")]),
+                                       t("test_gpu_decode.py")], order="random"),
         # kernels already validated on B200s, as a check of the emulator itself (golden vectors of the reference)
         "validated_kernels": _pytest(lib, [t("test_gpu_parity.py")],
                                      "wikipedia or taylorswift or small_cases or primitives or long_runs or table_growth or rescan"),
-        "splitter": _pytest(lib, [t("test_gpu_split.py")], "not piecewise"),
+        "splitter": _pytest(lib, [t("test_gpu_split.py")], "not piecewise", order="reverse"),
         # the sharded loop on 2..4 emulated GPUs (threads): NCCL-style collectives and the NVLink peer-memory kernels
         "sharded": subprocess.Popen([sys.executable, os.path.join(EMU, "emu_sharded.py"), "2:collective", "2:p2p", "3:p2p", "4:p2p"],
                                     cwd=ROOT, env=_env(lib), stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True),
