@@ -288,3 +288,55 @@ def encode_sharded(engine, data, offsets, merges, byte_perm=None, group=None, ga
     parts = [None] * world if rank == 0 else None
     dist.gather_object(ids, parts, dst=0, group=group)
     return np.concatenate(parts) if rank == 0 else None
+
+
+def encode_file(engine, path, merges, byte_perm=None, specials=None, group=None, gather=False, rank=None, world=None):
+    """regex.py:111-121 (with `specials`: regex.py:152-163) for a text FILE over `world` GPUs: every rank maps the file,
+    takes its byte range (shard_byte_range: cut where a letter is followed by a space — a chunk boundary whatever
+    surrounds it — and never inside a special token) and runs the fused split + encode on it
+    (Engine.encode_text_gpt4); chunks are independent, so there is no exchange.  Returns this rank's ids; with
+    gather=True rank 0 also gets the concatenation in text order (others: None).  The split pattern is the engine's
+    current one (BPE_OPT_SPLIT_PATTERN: GPT-4 by default)."""
+    if rank is None or world is None:
+        if dist.is_available() and dist.is_initialized():
+            rank, world = dist.get_rank(group), dist.get_world_size(group)
+        else:
+            rank, world = 0, 1
+    size = os.path.getsize(path)
+    mm = np.memmap(path, dtype=np.uint8, mode="r") if size else np.zeros(0, dtype=np.uint8)
+    toks = [t for t, _ in (specials or [])]
+
+    def inside_special(raw, p):
+        """does the cut between bytes p-1 and p fall strictly inside an occurrence of a special token?"""
+        return any(raw[p - j: p - j + len(t)] == t for t in toks for j in range(1, len(t)) if p - j >= 0)
+
+    def safe(window):
+        """first letter+space cut of the window that does not lie inside an occurrence of a special token, or -1"""
+        w = np.asarray(window, dtype=np.uint8)
+        raw, base = w.tobytes(), 0
+        while True:
+            p = first_safe_cut(w[base:])
+            if p < 0:
+                return -1
+            p += base
+            if not inside_special(raw, p):
+                return p
+            base = p
+
+    def cut(r):
+        if r <= 0:
+            return 0
+        if r >= world:
+            return size
+        lo = size * r // world
+        p = safe(mm[lo: min(size, lo + (1 << 20))])
+        if p < 0:
+            raise ValueError(f"no usable letter+space cut point in the MiB after offset {lo}: cannot shard this text")
+        return lo + p
+    lo, hi = cut(rank), cut(rank + 1)
+    ids = engine.encode_text_gpt4(mm[lo:hi], merges, byte_perm, specials=specials) if hi > lo else np.zeros(0, np.int32)
+    if not gather:
+        return ids
+    parts = [None] * world if rank == 0 else None
+    dist.gather_object(ids, parts, dst=0, group=group)
+    return np.concatenate(parts) if rank == 0 else None

@@ -361,6 +361,31 @@ class RegexTokenizer(Tokenizer):
         self.last_timing = eng.timing()
         self._adopt(pairs, counts, done, vocab_size - 256, verbose)
 
+    def encode_file(self, path, allowed_special="none", *, group=None, gather=False):
+        """encode() for a UTF-8 text file of any size (not in the reference, which takes a str: regex.py:123): the file is
+        memory-mapped; with torch.distributed initialised every rank encodes its own byte range and returns its own ids
+        (rank order = text order; gather=True concatenates them on rank 0).  GPT-2 / GPT-4 split patterns, special tokens
+        within the limits of the device front end.  "none_raise" is not offered: it would scan the file on the host."""
+        which = self._DEVICE_PATTERNS.get(self.compiled_pattern.pattern)
+        if which is None:
+            raise ValueError("encode_file splits on the device and supports the GPT-2 / GPT-4 split patterns only")
+        if allowed_special == "all":
+            special = self.special_tokens
+        elif allowed_special == "none":
+            special = {}
+        elif isinstance(allowed_special, set):
+            special = {k: v for k, v in self.special_tokens.items() if k in allowed_special}
+        else:
+            raise ValueError(f"allowed_special={allowed_special} not understood (encode_file takes 'all', 'none' or a set)")
+        if special and not self._device_specials(special):
+            raise ValueError("encode_file needs special tokens the device front end takes (at most 64, 1..48 utf-8 bytes each)")
+        from .dist import encode_file
+        from .engine import OPT_SPLIT_PATTERN
+        eng = self.engine
+        eng.set_option(OPT_SPLIT_PATTERN, which)
+        spec = [(k.encode("utf-8"), int(v)) for k, v in special.items()] or None
+        return encode_file(eng, path, self._merge_array(), self._byte_perm, spec, group=group, gather=gather)
+
     def register_special_tokens(self, special_tokens):
         self.special_tokens = special_tokens
         self.inverse_special_tokens = {idx: text for text, idx in special_tokens.items()}

@@ -48,3 +48,27 @@ def test_encode_sharded_concatenates_to_the_whole(taylorswift):
         parts = [encode_sharded(eng, data, offs, merges, rank=r, world=world) for r in range(world)]
         assert np.array_equal(np.concatenate(parts), want), world
     eng.close()
+
+
+def test_encode_file_shards_and_specials(tmp_path, taylorswift):
+    """RegexTokenizer.encode_file / dist.encode_file: byte-range shards cut at letter+space and never inside a special."""
+    from minbpe_b200 import RegexTokenizer
+    from minbpe_b200.dist import encode_file
+    tok = RegexTokenizer()
+    tok.train(taylorswift, 256 + 100)
+    tok.register_special_tokens({"<|endoftext|>": 100257, "<|im start|>": 100264})
+    # specials every ~3 KB, one kind containing letter+space, so that a naive cut could land inside one
+    body = taylorswift[:150000]
+    text = "".join(body[i:i + 3000] + ("<|im start|>" if (i // 3000) % 2 else "<|endoftext|>") for i in range(0, len(body), 3000))
+    p = tmp_path / "doc.txt"
+    p.write_bytes(text.encode("utf-8"))
+    want = tok.encode(text, allowed_special="all")
+    assert tok.encode_file(str(p), "all").tolist() == want
+    spec = [(k.encode("utf-8"), v) for k, v in tok.special_tokens.items()]
+    m = tok._merge_array()
+    for world in (2, 3, 5):
+        parts = [encode_file(tok.engine, str(p), m, None, spec, rank=r, world=world) for r in range(world)]
+        assert np.concatenate(parts).tolist() == want, world
+    assert tok.encode_file(str(p), "none").tolist() == tok.encode(text, allowed_special="none")
+    with pytest.raises(ValueError):
+        tok.encode_file(str(p), "none_raise")
