@@ -33,6 +33,7 @@ static u64 spec_fnv(const void *p, size_t n, u64 h = 0xcbf29ce484222325ull) {
 static int spec_set(bpe_handle *h, const uint8_t *bytes, const uint32_t *offsets, const int32_t *ids, int32_t k) {
     if (k < 0 || (k && (!bytes || !offsets || !ids))) return fail(h, BPE_ERR_ARG, "bad special-token arguments");
     if (k > SPEC_MAX) return fail(h, BPE_ERR_ARG, "more than 64 special tokens in one call");
+    if (k && offsets[0] != 0) return fail(h, BPE_ERR_ARG, "special_offsets[0] must be 0");
     for (int s = 0; s < k; ++s) {
         if (offsets[s + 1] <= offsets[s]) return fail(h, BPE_ERR_ARG, "special tokens must not be empty");
         if (offsets[s + 1] - offsets[s] > SPEC_MAX_LEN) return fail(h, BPE_ERR_ARG, "special tokens longer than 48 bytes are not handled on the device");
