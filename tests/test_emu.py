@@ -51,7 +51,7 @@ def jobs():
     procs = {
         # round-2 kernels that have not run on a GPU yet — memoised chunk encode (k_encode2.cuh), bpe_replay / resume, the
         # special-token front end (k_special.cuh), file / shard entry points — and bpe_decode
-        "new_kernels": _pytest(lib, [t("test_gpu_zy_encode2.py"), t("test_gpu_zz_resume.py"), t("test_gpu_zz_file.py"), t("test_gpu_zz_special.py"), t("test_gpu_zz_gpt2.py"), t("test_gpu_zz_gpt4.py"), t("test_gpu_zz_hist.py"),
+        "new_kernels": _pytest(lib, [t("test_gpu_zy_encode2.py"), t("test_gpu_zz_resume.py"), t("test_gpu_zz_file.py"), t("test_gpu_zz_special.py"), t("test_gpu_zz_gpt2.py"), t("test_gpu_zz_gpt4.py"), t("test_gpu_zz_hist.py"), t("test_gpu_zz_golden_r2.py"),
                                        t("test_gpu_decode.py")], order="random"),
         # kernels already validated on B200s, as a check of the emulator itself (golden vectors of the reference)
         "validated_kernels": _pytest(lib, [t("test_gpu_parity.py")],
