@@ -25,6 +25,13 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 EMU = os.path.join(ROOT, "tests", "emu")
 
 
+def _free_port():
+    import socket
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        return s.getsockname()[1]
+
+
 def _env(lib):
     env = dict(os.environ)
     env.update(BPE_LIB_PATH=lib, BPE_TEST_SMALL="1", EMU_SMS="2", PYTHONDONTWRITEBYTECODE="1")
@@ -69,7 +76,7 @@ def jobs():
     procs["bench1"] = subprocess.Popen([sys.executable, "bench.py", "--full-merges", "40"] + bench_args, cwd=ROOT, env=benv,
                                        stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True)
     procs["bench2"] = subprocess.Popen([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2",
-                                        "--master-addr", "127.0.0.1", "--master-port", "29547", "bench.py", "--gpus", "2"] + bench_args,
+                                        "--master-addr", "127.0.0.1", "--master-port", str(_free_port()), "bench.py", "--gpus", "2"] + bench_args,
                                        cwd=ROOT, env=benv, stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True)
     yield procs
     for p in procs.values():
