@@ -9,6 +9,7 @@
 
 #include <map>
 #include <mutex>
+#include <string>
 #include <vector>
 
 #if !defined(__x86_64__)
@@ -227,7 +228,14 @@ static void run_block(Sched *s, const LaunchCfg &cfg, dim3 bid) {
     }
 }
 
-void launch(const LaunchCfg &cfg, const std::function<void()> &body) {
+static std::mutex g_trace_mu;
+static std::map<std::string, unsigned long long> g_trace;
+
+void launch(const LaunchCfg &cfg, const char *kernel, const std::function<void()> &body) {
+    {
+        std::lock_guard<std::mutex> lk(g_trace_mu);
+        g_trace[kernel] += 1;
+    }
     Sched *s = sched();
     const unsigned n = cfg.block.x * cfg.block.y * cfg.block.z;
     if (n == 0 || n > MAX_THREADS) { fprintf(stderr, "emu: bad block size %u\n", n); abort(); }
@@ -315,3 +323,12 @@ cudaError_t cudaEventCreate(cudaEvent_t *e) { *e = new emu_event{0}; return cuda
 cudaError_t cudaEventDestroy(cudaEvent_t e) { delete e; return cudaSuccess; }
 cudaError_t cudaEventRecord(cudaEvent_t e, cudaStream_t) { e->t = now_ms(); return cudaSuccess; }
 cudaError_t cudaEventElapsedTime(float *ms, cudaEvent_t a, cudaEvent_t b) { *ms = (float)(b->t - a->t); return cudaSuccess; }
+
+extern "C" size_t emu_kernel_trace(char *buf, size_t cap) {
+    std::lock_guard<std::mutex> lk(emu::g_trace_mu);
+    std::string out;
+    for (auto &kv : emu::g_trace) { out += kv.first; out += '\n'; }
+    emu::g_trace.clear();
+    if (cap) { const size_t n = out.size() < cap - 1 ? out.size() : cap - 1; memcpy(buf, out.data(), n); buf[n] = 0; }
+    return out.size();
+}

@@ -71,14 +71,18 @@ struct LaunchCfg {
     dim3 grid, block; size_t smem; void *stream;
     LaunchCfg(dim3 g, dim3 b, size_t s = 0, void *st = nullptr) : grid(g), block(b), smem(s), stream(st) {}
 };
-void launch(const LaunchCfg &cfg, const std::function<void()> &body);
+void launch(const LaunchCfg &cfg, const char *kernel, const std::function<void()> &body);
 }  // namespace emu
+// names of the kernels launched by this process since the last call, one per line (tests/emu/kernel_coverage.py)
+extern "C" size_t emu_kernel_trace(char *buf, size_t cap);
 #define threadIdx (emu::ctx()->tid)
 #define blockIdx (emu::ctx()->bid)
 #define blockDim (emu::ctx()->bdim)
 #define gridDim (emu::ctx()->gdim)
 #define EMU_UNPAREN(...) __VA_ARGS__
-#define EMU_LAUNCH(K, CFG, ARGS) emu::launch(emu::LaunchCfg CFG, [&]() { EMU_UNPAREN K ARGS; })
+#define EMU_STR2(...) #__VA_ARGS__
+#define EMU_STR(...) EMU_STR2(__VA_ARGS__)
+#define EMU_LAUNCH(K, CFG, ARGS) emu::launch(emu::LaunchCfg CFG, EMU_STR(EMU_UNPAREN K), [&]() { EMU_UNPAREN K ARGS; })
 
 static inline void __syncthreads() { emu::sync_threads(); }
 static inline void __syncwarp(unsigned mask = 0xffffffffu) { emu::collective(emu::C_SYNC, mask, 0, 0); }
