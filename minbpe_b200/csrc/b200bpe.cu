@@ -594,7 +594,13 @@ static int hist_dense(bpe_handle *h, ull *dense_out) {
             CU(cudaMemsetAsync(h->dense2, 0, 65536 * 8, h->stream));
             CU(cudaMemsetAsync(h->d_cmp, 0, 4, h->stream));
             k_hist_dense<<<grid_old, 256, 0, h->stream>>>(h->buf[0], h->buf[1], h->ctl, h->edge[0], h->edge[1], dense_out, h->d_err);
+            CU(cudaGetLastError());
             k_hist_dense_packed<<<h->sms, HP_THREADS, HP_SMEM_BYTES, h->stream>>>(h->buf[0], h->buf[1], h->ctl, h->edge[0], h->edge[1], h->dense2, h->d_err);
+            if (cudaGetLastError() != cudaSuccess) {      // the launch itself was refused (a launch error is not sticky): keep k_hist_dense
+                h->tm.kernel_launches += 1;
+                h->tm.hist_kernel = 2;
+                return BPE_OK;
+            }
             k_dense_compare<<<65536 / 256, 256, 0, h->stream>>>(dense_out, h->dense2, h->d_cmp);
             h->tm.kernel_launches += 3;
             u32 differ = 1;
