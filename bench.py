@@ -960,7 +960,8 @@ def run_ours(args):
         "e2e": {"value": size * (W + K) / t_e2e / 1e9, "unit": "GB/s", "h2d_bytes_per_step": h2d / (W + K),
                 "d2h_bytes_per_step": d2h / (W + K), "seconds": t_e2e, "merges": W + K,
                 "load_seconds": t_load, "runs_seconds": [r[0] for r in e2e_runs], "host_buffer": "pinned (cudaHostRegister)" if pinned else "pageable",
-                "init_ms": tm_e2e["init_ms"], "hist_kernel": {1: "k_hist_dense_packed", 2: "k_hist_dense"}.get(int(tm_e2e["hist_kernel"]), "none"),
+                "init_ms": tm_e2e["init_ms"], "hist_kernel": {0: "k_hist_dense (choice still open)", 1: "k_hist_dense_packed (cross-checked and timed against k_hist_dense on this run's first stream)",
+                                2: "k_hist_dense (the packed kernel was slower or differed)"}.get(int(tm_e2e["hist_kernel"]), "?"),
                 "what": "bpe_load_text_gpt4(host text: H2D + GPT-4 split on the device) + bpe_train(W+K) + merges D2H, wall clock, median of 3 runs"},
         "first_pairs": pairs[:4].tolist(),
     }

@@ -243,8 +243,8 @@ typedef struct {
     uint64_t h2d_bytes;      /* host->device bytes copied by the last load/encode call */
     uint64_t d2h_bytes;      /* device->host bytes copied by the last train/encode/read call */
     uint64_t hist_kernel;    /* byte-pair histogram kernel of the last bpe_train / bpe_step_begin on a byte stream:
-                                1 = k_hist_dense_packed, 2 = k_hist_dense (the first use of a handle runs both and keeps
-                                the packed one only if all 65,536 counters agree), 0 = none run yet */
+                                1 = k_hist_dense_packed, 2 = k_hist_dense (BPE_OPT_HIST_KERNEL), 0 = k_hist_dense, the choice
+                                still open (no large stream seen yet) */
 } bpe_timing;
 int bpe_get_timing(bpe_handle *h, bpe_timing *out);
 
@@ -262,6 +262,9 @@ int bpe_get_timing(bpe_handle *h, bpe_timing *out);
                                    a piece are cut where a letter is followed by U+0020 (process-wide) */
 #define BPE_OPT_SPLIT_PATTERN 8 /* which of the reference's two split patterns (regex.py:18-19) the *_gpt4 entry points apply:
                                    0 = GPT4_SPLIT_PATTERN (default), 1 = GPT2_SPLIT_PATTERN; per handle */
+#define BPE_OPT_HIST_KERNEL 9   /* byte-pair histogram of iteration 0: 0 = k_hist_dense until the first stream of >= 8 Mi tokens,
+                                   where k_hist_dense_packed is cross-checked and timed against it and adopted if equal and
+                                   not slower (default); 1 = k_hist_dense_packed; 2 = k_hist_dense */
 int bpe_set_option(bpe_handle *h, int opt, int64_t value);
 
 /* Test hook: live entries (count > 0) of the incrementally maintained pair-count table, in no

@@ -74,6 +74,7 @@ struct bpe_handle {
     int opt_kernel_timing = 0, opt_rescan = 0, opt_batch = 256, opt_table_log2 = 0;
     int opt_memo_log2 = 0;   // BPE_OPT_ENC_MEMO_LOG2 (test hook): log2 slots of the encode memo table, 0 = default
     u32 opt_vocab_cap = 0;   // BPE_OPT_VOCAB_CAP: lower bound of the delta-vector layout V used by bpe_train
+    int opt_hist_kernel = 0;     // BPE_OPT_HIST_KERNEL: 0 = decide at the first large stream, 1 = k_hist_dense_packed, 2 = k_hist_dense
     int opt_split_pattern = 0;   // BPE_OPT_SPLIT_PATTERN: 0 = GPT-4 split pattern, 1 = GPT-2 (bpe_split_gpt4 / bpe_load_text_gpt4 / bpe_encode_text_gpt4*)
 
     bpe_timing tm = {};
@@ -237,6 +238,11 @@ extern "C" int bpe_set_option(bpe_handle *h, int opt, int64_t value) {
             h->opt_memo_log2 = (int)value;
             cudaSetDevice(h->device); cudaStreamSynchronize(h->stream);
             enc2_free(h);   // re-created with the new size by the next encode call
+            break;
+        case BPE_OPT_HIST_KERNEL:
+            if (value < 0 || value > 2) return fail(h, BPE_ERR_ARG, "hist kernel must be 0 (auto), 1 (packed) or 2 (hashed)");
+            h->opt_hist_kernel = (int)value;
+            if (value == 0) h->hist_mode = 0;
             break;
         case BPE_OPT_SPLIT_PATTERN:
             if (value != 0 && value != 1) return fail(h, BPE_ERR_ARG, "split pattern must be 0 (GPT-4) or 1 (GPT-2)");
@@ -581,22 +587,37 @@ static int ensure_delta(bpe_handle *h, u32 V) {
 // Byte-pair histogram of the current (byte) stream into dense_out[65536] (zeroed by the caller).
 // k_hist_dense_packed (dense 16-bit counters in 128 KB of shared memory) replaces k_hist_dense (hashed per-block table +
 // __match_any_sync folding, 19 ms per GiB).  It was written when no GPU was reachable and has only run on the CPU SIMT
-// emulator, so a handle's FIRST histogram runs both kernels and compares all 65,536 counters on the device: equal -> the
-// packed kernel from then on; different (or 128 KB of shared memory refused) -> k_hist_dense stays.  bpe_timing.hist_kernel
+// emulator, so a handle's first histogram of a LARGE stream (>= 8 Mi tokens; smaller ones just take k_hist_dense) runs both
+// kernels, timed with events, and compares all 65,536 counters on the device: equal and not slower -> the packed kernel
+// from then on; otherwise (or 128 KB of shared memory refused) -> k_hist_dense stays.  bpe_timing.hist_kernel
 // reports which one is in use.  (Drop the cross-check once `pytest -m gpu` has passed on a B200 with hist_kernel == 1.)
+#define HIST_DECIDE_MIN_TOKENS (8ull << 20)   /* smaller streams say nothing about speed: they take k_hist_dense, undecided */
 static int hist_dense(bpe_handle *h, ull *dense_out) {
     const int grid_old = h->sms * 3;
-    if (h->hist_mode == 0) {
+    if (h->opt_hist_kernel && h->hist_mode != h->opt_hist_kernel) {      // BPE_OPT_HIST_KERNEL: forced (tests)
+        if (h->opt_hist_kernel == 1 &&
+            cudaFuncSetAttribute(k_hist_dense_packed, cudaFuncAttributeMaxDynamicSharedMemorySize, HP_SMEM_BYTES) != cudaSuccess)
+            return fail(h, BPE_ERR_CUDA, "k_hist_dense_packed: 128 KB of shared memory refused");
+        h->hist_mode = h->opt_hist_kernel;
+    }
+    if (h->hist_mode == 0 && h->h_ctl->n >= HIST_DECIDE_MIN_TOKENS) {
         h->hist_mode = 2;
         if (cudaFuncSetAttribute(k_hist_dense_packed, cudaFuncAttributeMaxDynamicSharedMemorySize, HP_SMEM_BYTES) == cudaSuccess) {
             if (!h->dense2) CU(cudaMalloc(&h->dense2, 65536 * 8));
             if (!h->d_cmp) CU(cudaMalloc(&h->d_cmp, 4));
             CU(cudaMemsetAsync(h->dense2, 0, 65536 * 8, h->stream));
             CU(cudaMemsetAsync(h->d_cmp, 0, 4, h->stream));
+            cudaEvent_t ev[3] = {nullptr, nullptr, nullptr};
+            for (auto &e : ev) CU(cudaEventCreate(&e));
+            auto drop_events = [&]() { for (auto &e : ev) cudaEventDestroy(e); };
+            cudaEventRecord(ev[0], h->stream);
             k_hist_dense<<<grid_old, 256, 0, h->stream>>>(h->buf[0], h->buf[1], h->ctl, h->edge[0], h->edge[1], dense_out, h->d_err);
-            CU(cudaGetLastError());
+            cudaEventRecord(ev[1], h->stream);
+            if (cudaGetLastError() != cudaSuccess) { drop_events(); return fail(h, BPE_ERR_CUDA, "k_hist_dense launch failed"); }
             k_hist_dense_packed<<<h->sms, HP_THREADS, HP_SMEM_BYTES, h->stream>>>(h->buf[0], h->buf[1], h->ctl, h->edge[0], h->edge[1], h->dense2, h->d_err);
+            cudaEventRecord(ev[2], h->stream);
             if (cudaGetLastError() != cudaSuccess) {      // the launch itself was refused (a launch error is not sticky): keep k_hist_dense
+                drop_events();
                 h->tm.kernel_launches += 1;
                 h->tm.hist_kernel = 2;
                 return BPE_OK;
@@ -606,8 +627,12 @@ static int hist_dense(bpe_handle *h, ull *dense_out) {
             u32 differ = 1;
             cudaError_t e = cudaMemcpyAsync(&differ, h->d_cmp, 4, cudaMemcpyDeviceToHost, h->stream);
             if (e == cudaSuccess) e = cudaStreamSynchronize(h->stream);
+            float ms_old = 0, ms_new = 0;
+            if (e == cudaSuccess) { cudaEventElapsedTime(&ms_old, ev[0], ev[1]); cudaEventElapsedTime(&ms_new, ev[1], ev[2]); }
+            drop_events();
             if (e != cudaSuccess) return fail(h, BPE_ERR_CUDA, std::string("hist_dense: ") + cudaGetErrorString(e));
-            if (!differ) h->hist_mode = 1;
+            // adopted only when it gives the same 65,536 counters AND is not slower on this very stream
+            if (!differ && ms_new <= ms_old) h->hist_mode = 1;
             h->tm.hist_kernel = (uint64_t)h->hist_mode;
             return BPE_OK;      // dense_out holds k_hist_dense's result either way
         }
