@@ -6,8 +6,8 @@ The oracle side: host `regex` split of the same text -> distinct chunks in first
 multiplicities (oracle.c_dedup_chunks) -> oracle.c_train(weights=...), which
 tests/test_oracle.py::test_dedup_weights_equal_plain pins to the plain loop and to the reference.  ALL
 32,512 merges and their counts must agree (table growth, re-packing, the (a,a) path and the tie-breaks
-of a complete run are all inside).  Then a 64 MiB slice of another corpus is encoded with the resulting
-32k-entry table and compared with oracle.c_encode (regex.py:92-121).
+of a complete run are all inside).  A second test encodes a 64 MiB slice of another corpus with the resulting
+32k-entry table and compares it with oracle.c_encode (regex.py:92-121).
 
 Sizes can be reduced for a quick run: BPE_FULL_MIB (default 1024), BPE_FULL_MERGES (default 32512)."""
 import os
@@ -23,17 +23,24 @@ SIZE_MIB = int(os.environ.get("BPE_FULL_MIB", "1024"))
 MERGES = int(os.environ.get("BPE_FULL_MERGES", "32512"))
 
 
+_RUN = {}     # the trained tokenizer of the first test, reused by the second (training 1 GiB twice would double the run time)
+
+
+def _train_cfg3():
+    if "tok" not in _RUN:
+        from minbpe_b200 import RegexTokenizer
+        from minbpe_b200.synth import generate
+        raw = generate(1337, SIZE_MIB << 20)
+        tok = RegexTokenizer()
+        tok.train(raw.tobytes().decode("utf-8"), 256 + MERGES)                      # device split + device loop
+        _RUN.update(tok=tok, raw=raw, timing=tok.last_timing)
+    return _RUN["tok"], _RUN["raw"], _RUN["timing"]
+
+
 def test_cfg3_full_run_all_merges_vs_oracle():
-    from minbpe_b200 import RegexTokenizer
     from minbpe_b200.presplit import chunk_offsets
-    from minbpe_b200.synth import generate
     from minbpe_b200.tokenizer import GPT4_SPLIT_PATTERN
-    raw = generate(1337, SIZE_MIB << 20)
-    text = raw.tobytes().decode("utf-8")
-    tok = RegexTokenizer()
-    tok.train(text, 256 + MERGES)                      # device split + device loop
-    del text
-    tm = tok.last_timing
+    tok, raw, tm = _train_cfg3()
     got = np.array(list(tok.merges.keys()), dtype=np.int32)
     assert got.shape == (MERGES, 2)
     assert list(tok.merges.values()) == list(range(256, 256 + MERGES))
@@ -43,6 +50,7 @@ def test_cfg3_full_run_all_merges_vs_oracle():
     assert int(uw.sum()) == offs.size
     wp, wc, wn = oracle.c_train(ub.astype(np.int32), uo, MERGES, weights=uw)
     assert wn == MERGES
+    _RUN["wp"] = wp
     bad = np.flatnonzero((got != wp).any(axis=1))
     assert bad.size == 0, f"first differing merge {int(bad[0])}: got {got[bad[0]].tolist()} want {wp[bad[0]].tolist()}"
     # counts of every merge (stats[pair] before the merge, basic.py:45) through the engine API
@@ -58,13 +66,26 @@ def test_cfg3_full_run_all_merges_vs_oracle():
     for i in (0, MERGES // 2, MERGES - 1):
         a, b = wp[i].tolist()
         assert tok.vocab[256 + i] == tok.vocab[a] + tok.vocab[b]
-    # encode a slice of a DIFFERENT corpus (seed 1339 = cfg5's) with the full table, bit-exact ids
-    other = generate(1339, 64 << 20)
+
+
+def test_cfg3_table_encodes_another_corpus():
+    """A 64 MiB slice of a DIFFERENT corpus (seed 1339 = cfg5's) encoded with the full cfg3 table, bit-exact ids
+    (regex.py:111-121 through the class: fused split + memoised encode on the device), and decoded back."""
+    from minbpe_b200.presplit import chunk_offsets
+    from minbpe_b200.synth import generate
+    from minbpe_b200.tokenizer import GPT4_SPLIT_PATTERN
+    tok, _, _ = _train_cfg3()
+    merges = _RUN.get("wp")
+    if merges is None:
+        merges = np.array(list(tok.merges.keys()), dtype=np.int32)
+    other = generate(1339, min(64, 32 * SIZE_MIB) << 20)
     o2 = chunk_offsets(GPT4_SPLIT_PATTERN, other, workers=min(16, len(os.sched_getaffinity(0))))
-    ids = np.asarray(tok.encode_ordinary(other.tobytes().decode("utf-8")), dtype=np.int32)
-    want = oracle.c_encode(other, o2, wp)
+    text = other.tobytes().decode("utf-8")
+    ids = np.asarray(tok.encode_ordinary(text), dtype=np.int32)
+    want = oracle.c_encode(other, o2, merges)
     assert np.array_equal(ids, want)
-    assert tok.decode(ids[:100000].tolist()) == other.tobytes().decode("utf-8")[: len(tok.decode(ids[:100000].tolist()))]
+    head = tok.decode(ids[:100000].tolist())
+    assert head == text[: len(head)]
 
 
 def test_load_ids_above_255_then_train():
