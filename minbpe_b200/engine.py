@@ -115,6 +115,8 @@ class Engine:
             raise EngineError(f"bpe_create(device={device}) failed ({rc}): {self._lib.bpe_last_error(None).decode()}")
         self._h = h
         self.device = int(device)
+        if os.environ.get("BPE_HIST_KERNEL"):          # BPE_OPT_HIST_KERNEL for every engine of the process (0 auto, 1 packed, 2 hashed)
+            self.set_option(OPT_HIST_KERNEL, int(os.environ["BPE_HIST_KERNEL"]))
 
     def close(self):
         if getattr(self, "_h", None):

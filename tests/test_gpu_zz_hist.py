@@ -28,9 +28,10 @@ def test_packed_histogram_forced():
 
 
 def test_histogram_choice_is_made_on_a_large_stream_and_is_harmless():
-    from minbpe_b200.engine import Engine
+    from minbpe_b200 import engine as E
     from minbpe_b200.synth import generate
-    eng = Engine(0)
+    eng = E.Engine(0)
+    eng.set_option(E.OPT_HIST_KERNEL, 0)                    # the library's default (conftest pins the tests to k_hist_dense)
     raw = generate(1338, 9 << 20)
     eng.load_stream(raw[:100000], None)
     eng.train(3)
