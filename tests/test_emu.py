@@ -148,6 +148,7 @@ def test_emu_bench_one_rank_every_leg(jobs):
     assert d["full_run"]["parity_all_merges"] is True and d["full_run"]["merges"] == 40
     assert d["strong_cfg4"]["parity_vs_oracle"]["equal"] is True
     assert d["encode_cfg5"]["parity"]["equal"] is True and d["encode_cfg5"]["memo"]["fallback_pieces"] == 0
+    assert d["hist_packed"]["same_merges"] is True and d["e2e"]["hist_kernel"] == "k_hist_dense"
     test_emu_bench_one_rank_every_leg.sha = d["strong_cfg4"]["merges_sha16"]
 
 
