@@ -705,6 +705,34 @@ def encode_leg(args, eng, rank, world, merges):
     return res
 
 
+def filtered_run_leg(eng, raw, merges, want_pairs):
+    """BASELINE configs[2] to completion once more with the segment filter (BPE_OPT_SEG_FILTER = 1: from the batch after
+    merges have become sparse, per-segment id signatures decide which segments a merge can touch and k_merge_seg<true> works
+    through that list only).  Merges must equal those of full_run, which were checked against the oracle."""
+    from minbpe_b200 import engine as E
+    eng.set_option(E.OPT_KERNEL_TIMING, 0)
+    eng.set_option(E.OPT_SEG_FILTER, 1)
+    try:
+        dev_sync()
+        t0 = time.perf_counter()
+        eng.load_text_gpt4(raw)
+        pairs, counts, done = eng.train(merges)
+        dev_sync()
+        t_all = time.perf_counter() - t0
+        tm = eng.timing()
+    finally:
+        eng.set_option(E.OPT_SEG_FILTER, 0)
+        eng.set_option(E.OPT_KERNEL_TIMING, 1)
+    t_loop = tm["loop_ms"] / 1e3
+    return {"merges": int(done), "seconds": t_all, "loop_seconds": t_loop, "merges_per_s": done / t_loop,
+            "corpus_GBps": raw.size * done / t_loop / 1e9, "gpu_launches": int(tm["kernel_launches"]),
+            "filtered_segment_visits": int(tm["filter_segments"]),
+            "candidate_fraction": tm["filter_candidates"] / tm["filter_segments"] if tm["filter_segments"] else None,
+            "same_merges_as_full_run": bool(want_pairs is not None and done == len(want_pairs) and np.array_equal(pairs, want_pairs)),
+            "what": "bpe_load_text_gpt4 + bpe_train(all merges) with BPE_OPT_SEG_FILTER = 1; candidate_fraction = share of the segments "
+                    "the filtered merges had to read (the others cost an edge record and two signature words)"}
+
+
 def hist_leg(eng, raw, merges, want_pairs):
     """The e2e measurement again with the library's default choice of the iteration-0 histogram kernel: at this first large
     stream k_hist_dense_packed (dense 16-bit counters in shared memory; never run on hardware before this round's end) is
@@ -989,7 +1017,7 @@ def run_ours(args):
                      "peak_source": peak_src, "bytes_per_launch": (4.0 * n_in + 4.0 * n_out) / K, "ms_per_launch": k_ms,
                      "loop_frac_in_kernel": tm["merge_kernel_ms"] / tm["loop_ms"]},
         "cpu_baseline": cpu,
-        "full_run": None, "strong_cfg4": None, "encode_cfg5": None, "hist_packed": None,
+        "full_run": None, "strong_cfg4": None, "encode_cfg5": None, "full_run_filtered": None, "hist_packed": None,
         "e2e": {"value": size * (W + K) / t_e2e / 1e9, "unit": "GB/s", "h2d_bytes_per_step": h2d / (W + K),
                 "d2h_bytes_per_step": d2h / (W + K), "seconds": t_e2e, "merges": W + K,
                 "load_seconds": t_load, "runs_seconds": [r[0] for r in e2e_runs], "host_buffer": "pinned (cudaHostRegister)" if pinned else "pageable",
@@ -1017,6 +1045,8 @@ def run_ours(args):
             m = full_pairs if full_pairs is not None else merges_for_encode(eng, args.encode_merges, args.encode_train_mib)
             return encode_leg(args, eng, 0, 1, m)
         line["encode_cfg5"] = guarded("encode_cfg5", enc)
+    if args.full_merges > 0 and not args.no_filter_leg:
+        line["full_run_filtered"] = guarded("full_run_filtered", filtered_run_leg, eng, raw, args.full_merges, full_pairs)
     if not args.no_hist_leg:
         line["hist_packed"] = guarded("hist_packed", hist_leg, eng, raw, W + K, pairs_e2e)
     dog.disarm()
@@ -1116,6 +1146,7 @@ def main():
                     help="wall-clock budget of the optional legs (whole-loop run, cfg4, cfg5) after the contract line is complete; "
                          "when it runs out the line is printed with the legs finished so far")
     ap.add_argument("--no-hist-leg", action="store_true", help="skip the hist_packed leg (N=1)")
+    ap.add_argument("--no-filter-leg", action="store_true", help="skip the full_run_filtered leg (N=1)")
     ap.add_argument("--extras", action="store_true", help="side measurements (cfg2 wall time, encode throughput)")
     args = ap.parse_args()
     if args.warmup < 3 and args.impl == "ours":

@@ -245,6 +245,8 @@ typedef struct {
     uint64_t hist_kernel;    /* byte-pair histogram kernel of the last bpe_train / bpe_step_begin on a byte stream:
                                 1 = k_hist_dense_packed, 2 = k_hist_dense (BPE_OPT_HIST_KERNEL), 0 = k_hist_dense, the choice
                                 still open (no large stream seen yet) */
+    uint64_t filter_candidates; /* BPE_OPT_SEG_FILTER: segments the filtered merges of the last bpe_train had to look at ... */
+    uint64_t filter_segments;   /* ... of this many (sum over those merges of the number of segments); 0 = filter not used */
 } bpe_timing;
 int bpe_get_timing(bpe_handle *h, bpe_timing *out);
 
@@ -265,6 +267,9 @@ int bpe_get_timing(bpe_handle *h, bpe_timing *out);
 #define BPE_OPT_HIST_KERNEL 9   /* byte-pair histogram of iteration 0: 0 = k_hist_dense until the first stream of >= 8 Mi tokens,
                                    where k_hist_dense_packed is cross-checked and timed against it and adopted if equal and
                                    not slower (default); 1 = k_hist_dense_packed; 2 = k_hist_dense */
+#define BPE_OPT_SEG_FILTER 10   /* bpe_train: skip the segments a merge cannot touch (per-segment id signatures + candidate list,
+                                   k_seg_filter.cuh): 0 = off (default), 1 = from the batch after merges have become sparse
+                                   (fewer replacements per merge than a 32nd of the segments), 2 = always */
 int bpe_set_option(bpe_handle *h, int opt, int64_t value);
 
 /* Test hook: live entries (count > 0) of the incrementally maintained pair-count table, in no

@@ -16,6 +16,7 @@
 #include "k_merge.cuh"
 #include "k_merge_seg.cuh"
 #include "k_seg.cuh"
+#include "k_seg_filter.cuh"
 #include "k_stats.cuh"
 #include "k_encode.cuh"
 #include "k_split.cuh"
@@ -57,6 +58,10 @@ struct bpe_handle {
     ull *dense = nullptr;
     ull *dense2 = nullptr; u32 *d_cmp = nullptr;   // first-use cross-check of the packed histogram kernel (hist_dense)
     int hist_mode = 0;                             // 0 = not decided, 1 = k_hist_dense_packed, 2 = k_hist_dense
+    // segment filter (k_seg_filter.cuh): signatures, candidate list
+    u32 *sig = nullptr, *cand = nullptr; u64 sig_cap = 0;
+    bool filt_active = false;                      // the iterations being enqueued use the filter
+    bool sig_valid = false;                        // the signatures describe the current stream
     u32 *d_err = nullptr;
     int *log_pairs = nullptr; long long *log_counts = nullptr; int log_cap = 0;
     Best *partials = nullptr;
@@ -74,6 +79,7 @@ struct bpe_handle {
     int opt_kernel_timing = 0, opt_rescan = 0, opt_batch = 256, opt_table_log2 = 0;
     int opt_memo_log2 = 0;   // BPE_OPT_ENC_MEMO_LOG2 (test hook): log2 slots of the encode memo table, 0 = default
     u32 opt_vocab_cap = 0;   // BPE_OPT_VOCAB_CAP: lower bound of the delta-vector layout V used by bpe_train
+    int opt_seg_filter = 0;      // BPE_OPT_SEG_FILTER: 0 = off, 1 = switch it on when merges have become sparse, 2 = always
     int opt_hist_kernel = 0;     // BPE_OPT_HIST_KERNEL: 0 = decide at the first large stream, 1 = k_hist_dense_packed, 2 = k_hist_dense
     int opt_split_pattern = 0;   // BPE_OPT_SPLIT_PATTERN: 0 = GPT-4 split pattern, 1 = GPT-2 (bpe_split_gpt4 / bpe_load_text_gpt4 / bpe_encode_text_gpt4*)
 
@@ -172,9 +178,9 @@ extern "C" int bpe_create(int device, bpe_handle **out) {
     if (occ_same < 1) occ_same = 1;
     h->merge_grid_same = h->sms * occ_same;
     int occ_fast = 0;
-    if ((e = cudaFuncSetAttribute(k_merge_seg, cudaFuncAttributeMaxDynamicSharedMemorySize, MS_SMEM_BYTES)) != cudaSuccess)
+    if ((e = cudaFuncSetAttribute(k_merge_seg<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, MS_SMEM_BYTES)) != cudaSuccess)
         return bail("cudaFuncSetAttribute(k_merge_seg)", e);
-    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_fast, k_merge_seg, MS_THREADS, MS_SMEM_BYTES);
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_fast, k_merge_seg<false>, MS_THREADS, MS_SMEM_BYTES);
     if (occ_fast < 1) return bail("k_merge_seg does not fit on an SM", cudaErrorLaunchOutOfResources);
     h->merge_grid_seg = h->sms * occ_fast;
     h->argmax_grid = h->sms * 2;
@@ -198,6 +204,8 @@ extern "C" int bpe_destroy(bpe_handle *h) {
     if (h->desc) cudaFree(h->desc);
     for (int i = 0; i < 2; ++i) if (h->edge[i]) cudaFree(h->edge[i]);
     if (h->seg_offs) cudaFree(h->seg_offs);
+    if (h->sig) cudaFree(h->sig);
+    if (h->cand) cudaFree(h->cand);
     if (h->delta) cudaFree(h->delta);
     if (h->dense) cudaFree(h->dense);
     if (h->dense2) cudaFree(h->dense2);
@@ -238,6 +246,10 @@ extern "C" int bpe_set_option(bpe_handle *h, int opt, int64_t value) {
             h->opt_memo_log2 = (int)value;
             cudaSetDevice(h->device); cudaStreamSynchronize(h->stream);
             enc2_free(h);   // re-created with the new size by the next encode call
+            break;
+        case BPE_OPT_SEG_FILTER:
+            if (value < 0 || value > 2) return fail(h, BPE_ERR_ARG, "segment filter must be 0 (off), 1 (when sparse) or 2 (always)");
+            h->opt_seg_filter = (int)value; h->filt_active = false; h->sig_valid = false;
             break;
         case BPE_OPT_HIST_KERNEL:
             if (value < 0 || value > 2) return fail(h, BPE_ERR_ARG, "hist kernel must be 0 (auto), 1 (packed) or 2 (hashed)");
@@ -523,7 +535,8 @@ static void launch_merge(bpe_handle *h, ull *delta, int force, int same = -1, bo
         SegArgs S;
         S.ctl = h->ctl; S.buf0 = h->buf[0]; S.buf1 = h->buf[1]; S.e0 = h->edge[0]; S.e1 = h->edge[1];
         S.delta = delta; S.V = h->V; S.force = force; S.xbase = xbase; S.xstride = h->xchg_stride;
-        k_merge_seg<<<h->merge_grid_seg, MS_THREADS, MS_SMEM_BYTES, h->stream>>>(S);
+        if (h->filt_active) k_merge_seg<true><<<h->merge_grid_seg, MS_THREADS, MS_SMEM_BYTES, h->stream>>>(S);
+        else k_merge_seg<false><<<h->merge_grid_seg, MS_THREADS, MS_SMEM_BYTES, h->stream>>>(S);
         h->tm.kernel_launches += 1;
     }
     if (same != 0) {
@@ -534,6 +547,10 @@ static void launch_merge(bpe_handle *h, ull *delta, int force, int same = -1, bo
         k_merge<true><<<h->merge_grid_same, MG_THREADS, 0, h->stream>>>(A);
         h->tm.kernel_launches += 1;
         enqueue_edges_after_contig(h);
+        if (h->filt_active) {      // the pack moved tokens between segments: signatures from the tokens again (gated on a == b)
+            k_sig_build<<<h->sms * 8, 256, 0, h->stream>>>(h->buf[0], h->buf[1], h->ctl, h->edge[0], h->edge[1], h->sig, 1);
+            h->tm.kernel_launches += 1;
+        }
     }
 }
 
@@ -732,6 +749,38 @@ static void maybe_repack(bpe_handle *h) {
     if (2 * h->h_ctl->n >= nseg * (u64)SEG_TOKENS) return;
     enqueue_pack(h, 1);
     enqueue_edges_after_contig(h);
+    if (h->filt_active) {
+        k_sig_build<<<h->sms * 8, 256, 0, h->stream>>>(h->buf[0], h->buf[1], h->ctl, h->edge[0], h->edge[1], h->sig, 0);
+        h->tm.kernel_launches += 1;
+    }
+}
+
+// ---- segment filter (k_seg_filter.cuh) ---------------------------------------------------------------------------
+static void filt_rebuild(bpe_handle *h, int gate_same) {
+    k_sig_build<<<h->sms * 8, 256, 0, h->stream>>>(h->buf[0], h->buf[1], h->ctl, h->edge[0], h->edge[1], h->sig, gate_same);
+    h->tm.kernel_launches += 1;
+}
+
+// switch the filter on for the iterations enqueued from here on: storage, list address in the control block, signatures
+// of the stream as it is now
+static int filt_activate(bpe_handle *h) {
+    if (h->sig_cap < h->seg_cap) {
+        if (h->sig) cudaFree(h->sig);
+        if (h->cand) cudaFree(h->cand);
+        h->sig = nullptr; h->cand = nullptr; h->sig_cap = 0;
+        CU(cudaMalloc(&h->sig, h->seg_cap * SIG_WORDS * 4));
+        CU(cudaMalloc(&h->cand, h->seg_cap * 4));
+        h->sig_cap = h->seg_cap;
+    }
+    const u64 ptr = (u64)(uintptr_t)h->cand;
+    const u32 zero = 0;
+    CU(cudaMemcpyAsync(&h->ctl->cand_ptr, &ptr, 8, cudaMemcpyHostToDevice, h->stream));
+    CU(cudaMemcpyAsync(&h->ctl->n_cand, &zero, 4, cudaMemcpyHostToDevice, h->stream));
+    CU(cudaStreamSynchronize(h->stream));          // `ptr` / `zero` are stack variables
+    h->h_ctl->cand_ptr = ptr; h->h_ctl->n_cand = 0;
+    filt_rebuild(h, 0);
+    h->filt_active = true;
+    return BPE_OK;
 }
 
 static void enqueue_iteration(bpe_handle *h) {
@@ -743,15 +792,21 @@ static void enqueue_iteration(bpe_handle *h) {
         k_hist_hash<<<h->sms * 4, 256, 0, h->stream>>>(h->buf[0], h->buf[1], h->ctl, h->edge[0], h->edge[1], h->table, 1);
         h->tm.kernel_launches++;
     }
+    if (h->filt_active) { k_cand_reset<<<1, 1, 0, h->stream>>>(h->ctl); h->tm.kernel_launches++; }
     k_argmax<<<h->argmax_grid, 256, 0, h->stream>>>(h->table, h->ctl, h->partials, h->log_pairs, h->log_counts);
     k_find_first<<<h->ff_grid, 256, 0, h->stream>>>(h->buf[0], h->buf[1], h->edge[0], h->edge[1], h->table, h->ctl, h->log_pairs, h->log_counts, 0);
     h->tm.kernel_launches += 2;
+    if (h->filt_active) {    // candidate segments of the selected pair; k_merge_seg<true> works through that list only
+        k_seg_filter<<<h->sms * 8, 256, 0, h->stream>>>(h->ctl, h->edge[0], h->edge[1], h->edge[0], h->edge[1], h->sig, h->cand);
+        h->tm.kernel_launches++;
+    }
     if (h->opt_rescan) timed_merge(h, nullptr);
     else {
         timed_merge(h, h->delta);
         k_apply_delta<<<(h->V + 255) / 256, 256, 0, h->stream>>>(h->table, h->ctl, h->delta, h->V, 0, 0, 0, 1, 0);
         h->tm.kernel_launches++;
     }
+    if (h->filt_active) { k_sig_update<<<h->sms * 2, 256, 0, h->stream>>>(h->ctl, h->sig, h->cand, 1); h->tm.kernel_launches++; }
 }
 
 extern "C" int bpe_train(bpe_handle *h, int32_t num_merges, int32_t first_idx, int32_t *out_pairs, int64_t *out_counts,
@@ -800,6 +855,7 @@ extern "C" int bpe_train(bpe_handle *h, int32_t num_merges, int32_t first_idx, i
     if (bad) return fail(h, BPE_ERR_INTERNAL, "byte stream contains ids >= 256");
     h->h_ctl->iter = 0; h->h_ctl->done = 0; h->h_ctl->first_idx = (u32)first_idx; h->h_ctl->max_iter = (u32)num_merges;
     h->h_ctl->sum_in = 0; h->h_ctl->sum_out = 0;
+    h->h_ctl->cand_sum = 0; h->h_ctl->seg_sum = 0;
     h->h_ctl->overflow = 0;
     h->h_ctl->table_limit = (u64)(TABLE_MAX_LOAD * (double)(h->table.mask + 1));
     if ((rc = push_ctl(h))) return rc;
@@ -808,6 +864,9 @@ extern "C" int bpe_train(bpe_handle *h, int32_t num_merges, int32_t first_idx, i
     // ---- the merge loop: batches of iterations enqueued back to back, one host sync per batch ----
     int done_iters = 0;
     bool exhausted = false;
+    h->filt_active = false;
+    if (h->opt_seg_filter == 2 && !h->opt_rescan && (rc = filt_activate(h))) return rc;
+    u64 drops_seen = 0;
     while (done_iters < num_merges && !exhausted) {
         const int k = std::min(h->opt_batch, num_merges - done_iters);
         maybe_repack(h);
@@ -815,6 +874,14 @@ extern "C" int bpe_train(bpe_handle *h, int32_t num_merges, int32_t first_idx, i
         CU(cudaGetLastError());
         if ((rc = pull_ctl(h))) return rc;
         drain_kernel_events(h);
+        if (h->opt_seg_filter == 1 && !h->filt_active && !h->opt_rescan && (int)h->h_ctl->iter > done_iters) {
+            // BPE_OPT_SEG_FILTER = 1: once a merge replaces, on average, fewer tokens than a thirty-second of the segments
+            // there are, most segments cannot be touched by it: filter from the next batch on (merges only get sparser)
+            const u64 drops = h->h_ctl->sum_in - h->h_ctl->sum_out;
+            const u64 per_merge = (drops - drops_seen) / (u64)((int)h->h_ctl->iter - done_iters);
+            drops_seen = drops;
+            if (per_merge * 32 < h->h_ctl->nseg && (rc = filt_activate(h))) return rc;
+        }
         if (h->h_ctl->overflow) {
             if (h->opt_rescan) return fail(h, BPE_ERR_CAPACITY, "rescan mode: pair table too small (set BPE_OPT_TABLE_LOG2)");
             if ((rc = handle_overflow(h))) return rc;
@@ -831,6 +898,7 @@ extern "C" int bpe_train(bpe_handle *h, int32_t num_merges, int32_t first_idx, i
     h->tm.init_ms = ms01; h->tm.loop_ms = ms12;
     h->tm.tokens_in = h->h_ctl->sum_in; h->tm.tokens_out = h->h_ctl->sum_out;
     h->tm.table_slots = h->table.mask + 1; h->tm.table_used = h->h_ctl->table_used;
+    h->tm.filter_candidates = h->h_ctl->cand_sum; h->tm.filter_segments = h->h_ctl->seg_sum;
     if (done_iters > 0) {
         CU(cudaMemcpyAsync(out_pairs, h->log_pairs, (size_t)done_iters * 8, cudaMemcpyDeviceToHost, h->stream));
         CU(cudaMemcpyAsync(out_counts, h->log_counts, (size_t)done_iters * 8, cudaMemcpyDeviceToHost, h->stream));
@@ -838,6 +906,7 @@ extern "C" int bpe_train(bpe_handle *h, int32_t num_merges, int32_t first_idx, i
         h->tm.d2h_bytes = (u64)done_iters * 16;
     }
     *n_done = done_iters;
+    h->filt_active = false;      // the other users of launch_merge (bpe_merge, replay, the step API) do not maintain signatures
     h->table_valid = !h->opt_rescan;
     if (first_idx + done_iters > 256) h->bytes_only = false;
     if (done_iters > 0) h->max_id = std::max(h->max_id, (u32)(first_idx + done_iters - 1));

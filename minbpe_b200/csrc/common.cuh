@@ -95,6 +95,11 @@ struct Ctl {
     u64 table_limit;  // k_apply_delta stops inserting at this many occupied slots ...
     u32 overflow;     // ... and raises this; the host grows the table and re-runs the apply
     u32 tie_local;    // sharded loop: 1 = some pair tied at the max may occur in this rank's shard (k_tie_present)
+    // segment filter (k_seg_filter.cuh) — appended, so that the offsets every other kernel uses do not move
+    u32 n_cand;       // candidate segments of the merge in flight (entries of the list at cand_ptr)
+    u64 cand_ptr;     // device address of u32 cand[]
+    u64 cand_sum;     // sum of n_cand over the filtered merges of this bpe_train call (statistics)
+    u64 seg_sum;      // sum of nseg over the same merges
 };
 
 // ---- segmented stream ------------------------------------------------------------------------

@@ -133,6 +133,9 @@ __device__ __forceinline__ void scatter_row(u32 s_a, u32 lane, u32 off, u32 row_
     }
 }
 
+// LIST = false: every segment of the stream, MS_BATCH consecutive ones per ticket.  LIST = true: only the candidate segments
+// k_seg_filter put on the list at ctl->cand_ptr, one per ticket (the filter carried the other segments' edge records over).
+template <bool LIST>
 __global__ void __launch_bounds__(MS_THREADS, MS_MINBLOCKS) k_merge_seg(SegArgs A) {
     Ctl *ctl = A.ctl;
     if (!A.force && (ctl->done || ctl->overflow || ctl->iter >= ctl->max_iter)) return;
@@ -154,6 +157,8 @@ __global__ void __launch_bounds__(MS_THREADS, MS_MINBLOCKS) k_merge_seg(SegArgs 
     const u32 a = (u32)ctl->a, b = (u32)ctl->b, z = (u32)ctl->z;
     const u32 nseg = ctl->nseg;
     ull *const delta = A.xbase ? x_local_delta(A.xbase, A.xstride) : A.delta;
+    const u32 *__restrict__ cand = LIST ? reinterpret_cast<const u32 *>(ctl->cand_ptr) : nullptr;
+    const u32 n_cand = LIST ? ctl->n_cand : 0u;
 
     // this warp's private shared memory, as 32-bit shared-window byte addresses
     const u32 ws_a = smem_addr(s_warp + warp * MS_WARP_WORDS);   // [MS_STAGES][MS_SW] staging ring
@@ -188,10 +193,17 @@ __global__ void __launch_bounds__(MS_THREADS, MS_MINBLOCKS) k_merge_seg(SegArgs 
                 u32 tk = 0;
                 if (lane == 0) tk = atomicAdd(&ctl->merge_ticket, 1u);
                 tk = __shfl_sync(FULL, tk, 0);
-                if ((u64)tk * MS_BATCH >= nseg) { exhausted = true; continue; }
-                batch_seg = tk * MS_BATCH; batch_pos = 0;
-                if (lane < MS_BE) {
-                    const long long idx = (long long)batch_seg - 1 + lane;
+                if (LIST) {
+                    // one candidate per ticket: its record and its neighbours' go to the last three slots of the window,
+                    // so that the code below finds them where it finds those of the last segment of a batch
+                    if (tk >= n_cand) { exhausted = true; continue; }
+                    batch_seg = cand[tk] - (MS_BATCH - 1); batch_pos = MS_BATCH - 1;
+                } else {
+                    if ((u64)tk * MS_BATCH >= nseg) { exhausted = true; continue; }
+                    batch_seg = tk * MS_BATCH; batch_pos = 0;
+                }
+                if (LIST ? (lane >= MS_BATCH - 1 && lane < MS_BE) : (lane < MS_BE)) {
+                    const long long idx = (LIST ? (long long)(int)batch_seg : (long long)batch_seg) - 1 + lane;   // LIST: batch_seg may have wrapped below 0
                     uint4 q0, q1;   // f0 f1 f2 l0 | l1 count pad pad
                     if (idx >= 0 && idx < (long long)nseg) {
                         const uint4 *p = reinterpret_cast<const uint4 *>(&e_cur[idx]);

@@ -68,6 +68,7 @@ def jobs():
         "sharded": subprocess.Popen([sys.executable, os.path.join(EMU, "emu_sharded.py"), "2:collective", "2:p2p", "3:p2p", "4:p2p"],
                                     cwd=ROOT, env=_env(lib), stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True),
     }
+    procs["filter"] = _pytest(lib, [t("test_gpu_zz_filter.py")], order="random")
     procs["fuzz"] = subprocess.Popen([sys.executable, os.path.join(EMU, "emu_fuzz_encode.py"), "120", "7"], cwd=ROOT, env=_env(lib),
                                      stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
     bench_args = ["--size-mib", "1", "--steps", "6", "--warmup", "3", "--strong-mib", "2", "--strong-sparse-at", "24", "--strong-check", "16",
@@ -117,6 +118,11 @@ def test_emu_sharded_loop_collective_and_p2p(jobs):
     assert out.count("bit-exact on every rank") == 12
 
 
+def test_emu_segment_filter_training(jobs):
+    out = _finish(jobs, "filter")
+    assert " passed" in out and "failed" not in out
+
+
 def test_emu_encode_fuzz_under_guard_pages(jobs):
     assert "emu fuzz encode ok" in _finish(jobs, "fuzz")
 
@@ -149,6 +155,7 @@ def test_emu_bench_one_rank_every_leg(jobs):
     assert d["strong_cfg4"]["parity_vs_oracle"]["equal"] is True
     assert d["encode_cfg5"]["parity"]["equal"] is True and d["encode_cfg5"]["memo"]["fallback_pieces"] == 0
     assert d["hist_packed"]["same_merges"] is True and d["e2e"]["hist_kernel"] == "k_hist_dense"
+    assert d["full_run_filtered"]["same_merges_as_full_run"] is True and d["full_run_filtered"]["merges"] == 40
     test_emu_bench_one_rank_every_leg.sha = d["strong_cfg4"]["merges_sha16"]
 
 
