@@ -176,6 +176,7 @@ __global__ void __launch_bounds__(MS_THREADS, MS_MINBLOCKS) k_merge_seg(SegArgs 
 
     // ---- issue side: next non-empty segment of this warp -> bulk copy into `stage` ----
     u32 batch_seg = 0, batch_pos = MS_BATCH;   // warp-uniform
+    u32 list_next = blockIdx.x * MS_WARPS + warp;   // LIST: this warp's next entry of the candidate list
     // byte offset inside the batch's edge-record window (relative to record k) of the word lane l copies
     // into meta[l]: meta[0..4] = P0 P1 N0 N1 N2 = previous record's l[1], l[0], next record's f[0..2];
     // meta[8..15] = the segment's own record (for the untouched case); meta[5] = seg, meta[6] = count
@@ -191,14 +192,16 @@ __global__ void __launch_bounds__(MS_THREADS, MS_MINBLOCKS) k_merge_seg(SegArgs 
             }
             if (batch_pos == MS_BATCH) {
                 u32 tk = 0;
-                if (lane == 0) tk = atomicAdd(&ctl->merge_ticket, 1u);
-                tk = __shfl_sync(FULL, tk, 0);
                 if (LIST) {
-                    // one candidate per ticket: its record and its neighbours' go to the last three slots of the window,
-                    // so that the code below finds them where it finds those of the last segment of a batch
+                    // one candidate at a time, list entries dealt out round-robin over all warps of the grid (a ticket per
+                    // entry would be one atomic on one address per segment); its record and its neighbours' go to the last
+                    // three slots of the window, where the code below finds those of the last segment of a batch
+                    tk = list_next; list_next += gridDim.x * MS_WARPS;
                     if (tk >= n_cand) { exhausted = true; continue; }
                     batch_seg = cand[tk] - (MS_BATCH - 1); batch_pos = MS_BATCH - 1;
                 } else {
+                    if (lane == 0) tk = atomicAdd(&ctl->merge_ticket, 1u);
+                    tk = __shfl_sync(FULL, tk, 0);
                     if ((u64)tk * MS_BATCH >= nseg) { exhausted = true; continue; }
                     batch_seg = tk * MS_BATCH; batch_pos = 0;
                 }
