@@ -734,8 +734,7 @@ def filtered_run_leg(eng, raw, merges, want_pairs):
 
 
 def hist_leg(eng, raw, merges, want_pairs):
-    """The e2e measurement again with the library's default choice of the iteration-0 histogram kernel: at this first large
-    stream k_hist_dense_packed (dense 16-bit counters in shared memory; never run on hardware before this round's end) is
+    """The e2e measurement again with BPE_OPT_HIST_KERNEL = 0: at this first large stream k_hist_dense_packed (dense 16-bit counters in shared memory; never run on hardware before this round's end) is
     cross-checked and timed against k_hist_dense on the device and adopted if equal and not slower."""
     from minbpe_b200 import engine as E
     eng.set_option(E.OPT_HIST_KERNEL, 0)
@@ -756,7 +755,7 @@ def hist_leg(eng, raw, merges, want_pairs):
         return {"kernel": {1: "k_hist_dense_packed", 2: "k_hist_dense"}.get(chosen, str(chosen)), "e2e_seconds": sorted(runs)[1],
                 "e2e_GBps": raw.size * merges / sorted(runs)[1] / 1e9, "init_ms": sorted(init)[1],
                 "same_merges": bool(done == merges and np.array_equal(pairs, want_pairs)),
-                "what": "the e2e measurement of this line repeated with BPE_OPT_HIST_KERNEL = 0 (library default)"}
+                "what": "the e2e measurement of this line repeated with BPE_OPT_HIST_KERNEL = 0 (choose at the first large stream)"}
     finally:
         if pinned:
             unpin_host(raw)
@@ -949,8 +948,8 @@ def run_ours(args):
         torch.cuda.set_device(local)
     eng = E.Engine(local)
     eng.set_option(E.OPT_KERNEL_TIMING, 1)
-    # the contract line is measured on kernels that have run on B200s: the iteration-0 histogram with k_hist_dense; the
-    # library's default (cross-check + timing of k_hist_dense_packed at the first large stream) is the `hist_packed` leg below
+    # the contract line is measured on kernels that have run on B200s: the iteration-0 histogram with k_hist_dense (the
+    # library's default); the automatic choice (cross-check + timing of k_hist_dense_packed) is the `hist_packed` leg below
     eng.set_option(E.OPT_HIST_KERNEL, 2)
 
     sampler = ClockSampler(local)

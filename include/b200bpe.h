@@ -264,9 +264,9 @@ int bpe_get_timing(bpe_handle *h, bpe_timing *out);
                                    a piece are cut where a letter is followed by U+0020 (process-wide) */
 #define BPE_OPT_SPLIT_PATTERN 8 /* which of the reference's two split patterns (regex.py:18-19) the *_gpt4 entry points apply:
                                    0 = GPT4_SPLIT_PATTERN (default), 1 = GPT2_SPLIT_PATTERN; per handle */
-#define BPE_OPT_HIST_KERNEL 9   /* byte-pair histogram of iteration 0: 0 = k_hist_dense until the first stream of >= 8 Mi tokens,
-                                   where k_hist_dense_packed is cross-checked and timed against it and adopted if equal and
-                                   not slower (default); 1 = k_hist_dense_packed; 2 = k_hist_dense */
+#define BPE_OPT_HIST_KERNEL 9   /* byte-pair histogram of iteration 0: 2 = k_hist_dense (default: the kernel that has run on B200s);
+                                   1 = k_hist_dense_packed; 0 = k_hist_dense until the first stream of >= 8 Mi tokens, where
+                                   k_hist_dense_packed is cross-checked and timed against it and adopted if equal and not slower */
 #define BPE_OPT_SEG_FILTER 10   /* bpe_train: skip the segments a merge cannot touch (per-segment id signatures + candidate list,
                                    k_seg_filter.cuh): 0 = off (default), 1 = from the batch after merges have become sparse
                                    (fewer replacements per merge than a 32nd of the segments), 2 = always */

@@ -80,7 +80,8 @@ struct bpe_handle {
     int opt_memo_log2 = 0;   // BPE_OPT_ENC_MEMO_LOG2 (test hook): log2 slots of the encode memo table, 0 = default
     u32 opt_vocab_cap = 0;   // BPE_OPT_VOCAB_CAP: lower bound of the delta-vector layout V used by bpe_train
     int opt_seg_filter = 0;      // BPE_OPT_SEG_FILTER: 0 = off, 1 = switch it on when merges have become sparse, 2 = always
-    int opt_hist_kernel = 0;     // BPE_OPT_HIST_KERNEL: 0 = decide at the first large stream, 1 = k_hist_dense_packed, 2 = k_hist_dense
+    int opt_hist_kernel = 2;     // BPE_OPT_HIST_KERNEL: 2 = k_hist_dense (default: the kernel that has run on B200s), 1 = k_hist_dense_packed,
+                                 // 0 = decide at the first large stream (cross-check + timing)
     int opt_split_pattern = 0;   // BPE_OPT_SPLIT_PATTERN: 0 = GPT-4 split pattern, 1 = GPT-2 (bpe_split_gpt4 / bpe_load_text_gpt4 / bpe_encode_text_gpt4*)
 
     bpe_timing tm = {};

@@ -4,10 +4,8 @@ import sys
 
 import pytest
 
-# The GPU tests run the byte-pair histogram of iteration 0 with k_hist_dense, the kernel that has run on B200s: the library's
-# own default would cross-check and time the never-run k_hist_dense_packed against it in whichever test first trains on
-# >= 8 Mi tokens (the cfg3 test, second in the order below).  tests/test_gpu_zz_hist.py — last group — selects the packed
-# kernel and the automatic choice explicitly; bench.py runs the library's default.
+# The GPU tests run the byte-pair histogram of iteration 0 with k_hist_dense, the kernel that has run on B200s (also the
+# library's default); tests/test_gpu_zz_hist.py — last group — selects the packed kernel and the automatic choice explicitly.
 os.environ.setdefault("BPE_HIST_KERNEL", "2")
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))

@@ -1,7 +1,7 @@
 """GPU: the packed dense byte-pair histogram (k_hist_dense_packed, b200bpe.cu hist_dense).  Forced on
-(BPE_OPT_HIST_KERNEL = 1) it must train exactly like the oracle; left to itself the library decides at the first large
-stream — both kernels run, the 65,536 counters are compared on the device and the launches timed — and whatever it
-decides, results do not change."""
+(BPE_OPT_HIST_KERNEL = 1) it must train exactly like the oracle; with BPE_OPT_HIST_KERNEL = 0 the library decides at the
+first large stream — both kernels run, the 65,536 counters are compared on the device and the launches timed — and
+whatever it decides, results do not change.  (Default: 2, the kernel that has run on B200s.)"""
 import numpy as np
 import pytest
 
@@ -31,7 +31,7 @@ def test_histogram_choice_is_made_on_a_large_stream_and_is_harmless():
     from minbpe_b200 import engine as E
     from minbpe_b200.synth import generate
     eng = E.Engine(0)
-    eng.set_option(E.OPT_HIST_KERNEL, 0)                    # the library's default (conftest pins the tests to k_hist_dense)
+    eng.set_option(E.OPT_HIST_KERNEL, 0)                    # decide at the first large stream (the default is k_hist_dense)
     raw = generate(1338, 9 << 20)
     eng.load_stream(raw[:100000], None)
     eng.train(3)
