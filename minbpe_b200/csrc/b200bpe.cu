@@ -807,7 +807,10 @@ static void enqueue_iteration(bpe_handle *h) {
         k_apply_delta<<<(h->V + 255) / 256, 256, 0, h->stream>>>(h->table, h->ctl, h->delta, h->V, 0, 0, 0, 1, 0);
         h->tm.kernel_launches++;
     }
-    if (h->filt_active) { k_sig_update<<<h->sms * 2, 256, 0, h->stream>>>(h->ctl, h->sig, h->cand, 1); h->tm.kernel_launches++; }
+    if (h->filt_active) {    // the listed segments may have changed: their signatures from their tokens again
+        k_sig_rebuild_cand<<<h->sms * 4, 256, 0, h->stream>>>(h->ctl, h->buf[0], h->buf[1], h->edge[0], h->edge[1], h->sig, h->cand);
+        h->tm.kernel_launches++;
+    }
 }
 
 extern "C" int bpe_train(bpe_handle *h, int32_t num_merges, int32_t first_idx, int32_t *out_pairs, int64_t *out_counts,
