@@ -765,13 +765,14 @@ static void filt_rebuild(bpe_handle *h, int gate_same) {
 // switch the filter on for the iterations enqueued from here on: storage, list address in the control block, signatures
 // of the stream as it is now
 static int filt_activate(bpe_handle *h) {
-    if (h->sig_cap < h->seg_cap) {
+    const u64 want = (u64)h->h_ctl->nseg + 64;      // segments of the stream as it is now (the count only ever falls), not the buffers' capacity
+    if (h->sig_cap < want) {
         if (h->sig) cudaFree(h->sig);
         if (h->cand) cudaFree(h->cand);
         h->sig = nullptr; h->cand = nullptr; h->sig_cap = 0;
-        CU(cudaMalloc(&h->sig, h->seg_cap * SIG_WORDS * 4));
-        CU(cudaMalloc(&h->cand, h->seg_cap * 4));
-        h->sig_cap = h->seg_cap;
+        CU(cudaMalloc(&h->sig, want * SIG_WORDS * 4));
+        CU(cudaMalloc(&h->cand, want * 4));
+        h->sig_cap = want;
     }
     const u64 ptr = (u64)(uintptr_t)h->cand;
     const u32 zero = 0;
