@@ -761,6 +761,36 @@ def hist_leg(eng, raw, merges, want_pairs):
             unpin_host(raw)
 
 
+def p2p_leg(eng, step, rank, world, raw, offs, W, K, want_pairs, collective_ms):
+    """The timed K merges of the sharded line again with exchange = "p2p": candidate push on ties + delta pull/sum fused
+    with the table update, over CUDA-IPC peer memory, no NCCL call per merge (k_xchg_cand / k_xchg_apply, bpe_step_fused).
+    Set-up includes a handshake kernel; if peer memory cannot be used the ranks agree on that and the leg says why."""
+    import torch.distributed as dist
+    from minbpe_b200.dist import ShardedTrainer
+    eng.load_stream(raw, offs)
+    tr = ShardedTrainer(step, rank, world, poll_every=16, exchange="p2p")
+    tr.prepare(W + K)
+    if tr.exchange != "p2p":
+        return {"used": False, "reason": getattr(tr, "exchange_fallback", None)}
+    tr.run(W)
+    dev_sync(); dist.barrier(); dev_sync()
+    ev0, ev1 = new_event(), new_event()
+    ev0.record(step.stream)
+    tr.run(K)
+    ev1.record(step.stream)
+    dev_sync(); dist.barrier(); dev_sync()
+    t = dev_tensor([ev0.elapsed_time(ev1) / 1e3])
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    pairs, _, n = tr.result()
+    same = dev_tensor([1.0 if (n == W + K and np.array_equal(pairs[: W + K], want_pairs)) else 0.0])
+    dist.all_reduce(same, op=dist.ReduceOp.MIN)
+    step.e.xchg_detach()
+    dev_sync(); dist.barrier(); dev_sync()
+    ms = float(t.item()) / K * 1e3
+    return {"used": True, "ms_per_step": ms, "collective_ms_per_step": collective_ms, "same_merges_as_collective": bool(same.item() > 0.5),
+            "what": "merge steps W..W+K-1 of the same shards, CUDA events on the shared stream, max over ranks"}
+
+
 def merges_for_encode(eng, n_merges, train_mib=256):
     """A trained table for the encode leg when the run has none yet: RegexTokenizer.train on 256 MiB of the cfg3 corpus."""
     from minbpe_b200.synth import generate
@@ -887,7 +917,7 @@ def run_sharded(args, rank, world, local):
                          "achieved": bytes_per_launch / (k_ms / 1e3) / 1e9, "peak": peak, "unit": "GB/s",
                          "frac": bytes_per_launch / (k_ms / 1e3) / 1e9 / peak, "traffic": None, "peak_source": peak_src, "ms_per_launch": k_ms},
             "cpu_baseline": None,
-            "strong_cfg4": None, "encode_cfg5": None,
+            "strong_cfg4": None, "encode_cfg5": None, "p2p_trial": None,
             "e2e": {"value": size * world * (W + K) / float(t_e2e.item()) / 1e9, "unit": "GB/s",
                     "h2d_bytes_per_step": h2d / (W + K), "d2h_bytes_per_step": 16.0, "seconds": float(t_e2e.item()),
                     "host_buffer": "pinned (cudaHostRegister)" if pinned else "pageable",
@@ -902,17 +932,20 @@ def run_sharded(args, rank, world, local):
         unpin_host(raw)
     strong = guarded("strong_cfg4", strong_leg, args, eng, rank, world, local) if (args.strong_gib > 0 or args.strong_mib > 0) else None
     enc = guarded("encode_cfg5", lambda: encode_leg(args, eng, rank, world, merges_for_encode(eng, args.encode_merges, args.encode_train_mib))) if args.encode_gb > 0 else None
+    # last: the same K merges once more with the per-merge exchanges done by our NVLink peer-memory kernels (k_xchg.cuh)
+    # instead of the two NCCL calls — a trial: those kernels have only run on the CPU emulator
+    p2p = None
+    if not EMU and not args.no_p2p_trial and args.exchange != "p2p":
+        p2p = guarded("p2p_trial", p2p_leg, eng, step, rank, world, raw, offs, W, K, pairs[: W + K],
+                      float(t_loop.item()) / K * 1e3 if rank == 0 else 0.0)
     dog.disarm()
     if rank == 0:
-        line["strong_cfg4"], line["encode_cfg5"] = strong, enc
+        line["strong_cfg4"], line["encode_cfg5"], line["p2p_trial"] = strong, enc, p2p
         print(json.dumps(line), flush=True)
-    try:
-        step.e.xchg_detach()
-        sync_all()
-        eng.close()
-        dist.destroy_process_group()
-    except Exception:  # noqa: BLE001
-        pass
+    # The line is out.  Leave without tearing NCCL and the peer mappings down: after a leg that died half-way on some rank a
+    # collective in the teardown would wait for that rank until NCCL's own timeout; process exit releases everything.
+    sys.stdout.flush()
+    os._exit(0)
 
 
 # ---------------------------------------------------------------------------------------------
@@ -1145,6 +1178,7 @@ def main():
                     help="wall-clock budget of the optional legs (whole-loop run, cfg4, cfg5) after the contract line is complete; "
                          "when it runs out the line is printed with the legs finished so far")
     ap.add_argument("--no-hist-leg", action="store_true", help="skip the hist_packed leg (N=1)")
+    ap.add_argument("--no-p2p-trial", action="store_true", help="N>1: skip the trial of the NVLink peer-memory exchange kernels")
     ap.add_argument("--no-filter-leg", action="store_true", help="skip the full_run_filtered leg (N=1)")
     ap.add_argument("--extras", action="store_true", help="side measurements (cfg2 wall time, encode throughput)")
     args = ap.parse_args()
