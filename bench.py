@@ -934,13 +934,18 @@ def run_sharded(args, rank, world, local):
     enc = guarded("encode_cfg5", lambda: encode_leg(args, eng, rank, world, merges_for_encode(eng, args.encode_merges, args.encode_train_mib))) if args.encode_gb > 0 else None
     # last: the same K merges once more with the per-merge exchanges done by our NVLink peer-memory kernels (k_xchg.cuh)
     # instead of the two NCCL calls — a trial: those kernels have only run on the CPU emulator
-    p2p = None
-    if not EMU and not args.no_p2p_trial and args.exchange != "p2p":
-        p2p = guarded("p2p_trial", p2p_leg, eng, step, rank, world, raw, offs, W, K, pairs[: W + K],
-                      float(t_loop.item()) / K * 1e3 if rank == 0 else 0.0)
     dog.disarm()
     if rank == 0:
-        line["strong_cfg4"], line["encode_cfg5"], line["p2p_trial"] = strong, enc, p2p
+        line["strong_cfg4"], line["encode_cfg5"] = strong, enc
+    p2p = None
+    if not EMU and not args.no_p2p_trial and args.exchange != "p2p":
+        dog2 = Watchdog(min(120, args.leg_budget_s))     # its own, short budget: a rank that fails alone leaves the others in a collective
+        dog2.arm(line)
+        p2p = guarded("p2p_trial", p2p_leg, eng, step, rank, world, raw, offs, W, K, pairs[: W + K],
+                      float(t_loop.item()) / K * 1e3 if rank == 0 else 0.0)
+        dog2.disarm()
+    if rank == 0:
+        line["p2p_trial"] = p2p
         print(json.dumps(line), flush=True)
     # The line is out.  Leave without tearing NCCL and the peer mappings down: after a leg that died half-way on some rank a
     # collective in the teardown would wait for that rank until NCCL's own timeout; process exit releases everything.
