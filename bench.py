@@ -767,6 +767,9 @@ def p2p_leg(eng, step, rank, world, raw, offs, W, K, want_pairs, collective_ms):
     Set-up includes a handshake kernel; if peer memory cannot be used the ranks agree on that and the leg says why."""
     import torch.distributed as dist
     from minbpe_b200.dist import ShardedTrainer
+    # the strong leg bound the engine to the stream of its own step engine: back to this one's, on which the events below
+    # are recorded and torch issues the collectives of prepare()
+    step.e.set_stream(step.stream.cuda_stream)
     eng.load_stream(raw, offs)
     tr = ShardedTrainer(step, rank, world, poll_every=16, exchange="p2p")
     tr.prepare(W + K)
