@@ -24,7 +24,7 @@ def _stale(target, sources):
 
 
 def build(force=False, verbose=False):
-    cu_sources = [os.path.join(HERE, f) for f in os.listdir(HERE) if f.endswith((".cu", ".cuh", ".inl"))]
+    cu_sources = [os.path.join(HERE, f) for f in os.listdir(HERE) if f.endswith((".cu", ".cuh", ".inl", ".h"))]
     cu_sources.append(os.path.join(HERE, "..", "..", "include", "b200bpe.h"))
     so = os.path.join(HERE, "libb200bpe.so")
     if force or _stale(so, cu_sources):
