@@ -163,6 +163,45 @@ class Watchdog:
             self.timer.cancel()
 
 
+def host_mem_available():
+    """Bytes of host memory this process can still take: /proc/meminfo MemAvailable, capped by the cgroup's limit - usage."""
+    avail = None
+    try:
+        for ln in open("/proc/meminfo"):
+            if ln.startswith("MemAvailable:"):
+                avail = int(ln.split()[1]) * 1024
+                break
+    except OSError:
+        pass
+    for lim, cur in (("/sys/fs/cgroup/memory.max", "/sys/fs/cgroup/memory.current"),
+                     ("/sys/fs/cgroup/memory/memory.limit_in_bytes", "/sys/fs/cgroup/memory/memory.usage_in_bytes")):
+        try:
+            l = open(lim).read().strip()
+            if l != "max" and int(l) < (1 << 60):
+                room = int(l) - int(open(cur).read().strip())
+                avail = room if avail is None else min(avail, room)
+        except (OSError, ValueError):
+            pass
+    return avail
+
+
+def host_room_for(name, need_bytes, world=1):
+    """None if the box has room for an optional leg's host buffers (with a 2x margin), else a {"skipped": ...} entry.
+    Under torchrun rank 0 decides for everybody (the legs contain collectives)."""
+    avail = host_mem_available()
+    ok = 1 if (avail is None or avail >= 2 * need_bytes) else 0
+    if world > 1:
+        import torch
+        import torch.distributed as dist
+        t = dev_tensor([ok], dtype=torch.int64)
+        dist.broadcast(t, src=0)
+        ok = int(t.item())
+    if ok:
+        return None
+    return {"skipped": f"{name}: needs {need_bytes / 1e9:.1f} GB of host memory for its buffers, "
+                       f"{(avail or 0) / 1e9:.1f} GB available on this box (2x margin required)"}
+
+
 def guarded(name, fn, *a):
     """Run an optional leg; a failure becomes {"error": ...} in the line instead of losing the whole run."""
     try:
@@ -474,6 +513,17 @@ def oracle_train_unique(chunks, weights, merges):
 def merges_sha(pairs):
     import hashlib
     return hashlib.sha256(np.ascontiguousarray(pairs, dtype=np.int32).tobytes()).hexdigest()[:16]
+
+
+def strong_host_bytes(args):
+    """Host memory of the cfg4 leg over all ranks of the box: the corpus itself (the shards add up to it)."""
+    return (args.strong_mib << 20) if args.strong_mib else (args.strong_gib << 30)
+
+
+def encode_host_bytes(args):
+    """Host memory of the cfg5 leg over all ranks: the text + an id buffer of up to 4 B per text byte (small tables)."""
+    n = int(args.encode_gb * 1e9)
+    return n + 4 * (n // 2 if args.encode_merges >= 8192 else n)
 
 
 def strong_leg(args, eng, rank, world, local):
@@ -933,8 +983,13 @@ def run_sharded(args, rank, world, local):
     dog.arm(line)
     if pinned:
         unpin_host(raw)
-    strong = guarded("strong_cfg4", strong_leg, args, eng, rank, world, local) if (args.strong_gib > 0 or args.strong_mib > 0) else None
-    enc = guarded("encode_cfg5", lambda: encode_leg(args, eng, rank, world, merges_for_encode(eng, args.encode_merges, args.encode_train_mib))) if args.encode_gb > 0 else None
+    strong, enc = None, None
+    if args.strong_gib > 0 or args.strong_mib > 0:
+        strong = host_room_for("strong_cfg4", strong_host_bytes(args), world) or \
+            guarded("strong_cfg4", strong_leg, args, eng, rank, world, local)
+    if args.encode_gb > 0:
+        enc = host_room_for("encode_cfg5", encode_host_bytes(args), world) or \
+            guarded("encode_cfg5", lambda: encode_leg(args, eng, rank, world, merges_for_encode(eng, args.encode_merges, args.encode_train_mib)))
     # last: the same K merges once more with the per-merge exchanges done by our NVLink peer-memory kernels (k_xchg.cuh)
     # instead of the two NCCL calls — a trial: those kernels have only run on the CPU emulator
     dog.disarm()
@@ -1079,12 +1134,13 @@ def run_ours(args):
         else:
             line["full_run"] = r
     if args.strong_gib > 0 or args.strong_mib > 0:
-        line["strong_cfg4"] = guarded("strong_cfg4", strong_leg, args, eng, 0, 1, local)
+        line["strong_cfg4"] = host_room_for("strong_cfg4", strong_host_bytes(args)) or \
+            guarded("strong_cfg4", strong_leg, args, eng, 0, 1, local)
     if args.encode_gb > 0:
         def enc():
             m = full_pairs if full_pairs is not None else merges_for_encode(eng, args.encode_merges, args.encode_train_mib)
             return encode_leg(args, eng, 0, 1, m)
-        line["encode_cfg5"] = guarded("encode_cfg5", enc)
+        line["encode_cfg5"] = host_room_for("encode_cfg5", encode_host_bytes(args)) or guarded("encode_cfg5", enc)
     if args.full_merges > 0 and not args.no_filter_leg:
         line["full_run_filtered"] = guarded("full_run_filtered", filtered_run_leg, eng, raw, args.full_merges, full_pairs)
     if not args.no_hist_leg:
