@@ -76,22 +76,23 @@ static int enc2_prepare(bpe_handle *h, const int32_t *merges, int32_t n_merges, 
     if (!h->enc) h->enc = new (std::nothrow) EncState();
     EncState *S = h->enc;
     if (!S) return fail(h, BPE_ERR_INTERNAL, "out of host memory");
-    if (!S->memo) {
+    if (!S->memo || !S->pool || !S->new_list || !S->ctl || !S->d_total || !S->d_perm) {   // (an earlier call may have run out of memory half-way)
         S->memo_cap = 1ull << (h->opt_memo_log2 ? h->opt_memo_log2 : ENC2_MEMO_LOG2);
-        E2CU(cudaMalloc(&S->memo, S->memo_cap * sizeof(MemoSlot)));
         S->pool_cap = ENC2_POOL_IDS;
-        E2CU(cudaMalloc(&S->pool, S->pool_cap * 4));
-        E2CU(cudaMalloc(&S->new_list, S->memo_cap * 4));
-        E2CU(cudaMalloc(&S->ctl, sizeof(EncCtl)));
-        E2CU(cudaMalloc(&S->d_total, 8));
-        E2CU(cudaMalloc(&S->d_perm, 256));
         S->n_merges = -1;
+        if (!S->memo) E2CU(cudaMalloc(&S->memo, S->memo_cap * sizeof(MemoSlot)));
+        if (!S->pool) E2CU(cudaMalloc(&S->pool, S->pool_cap * 4));
+        if (!S->new_list) E2CU(cudaMalloc(&S->new_list, S->memo_cap * 4));
+        if (!S->ctl) E2CU(cudaMalloc(&S->ctl, sizeof(EncCtl)));
+        if (!S->d_total) E2CU(cudaMalloc(&S->d_total, 8));
+        if (!S->d_perm) E2CU(cudaMalloc(&S->d_perm, 256));
     }
     const u64 mh = fnv64(merges, (size_t)n_merges * 8), ph = perm ? fnv64(perm, 256) : 0;
     const u64 sh = (use_spec && h->spec && h->spec->k) ? h->spec->hash : 0;
     if (S->n_merges == n_merges && S->merges_hash == mh && S->has_perm == (perm != nullptr) && S->perm_hash == ph && S->spec_hash == sh)
         return BPE_OK;
     S->spec_hash = sh;
+    S->n_merges = -1;                         // nothing is valid until the end of this function
     const u64 tcap = next_pow2(std::max<u64>(1024, 4ull * (u64)n_merges));
     if (tcap > S->rt_cap) {
         cudaFree(S->d_rkeys); cudaFree(S->d_rranks); cudaFree(S->d_merges);
@@ -229,7 +230,10 @@ static int enc2_piece(bpe_handle *h, const unsigned char *d_text, const unsigned
         *fell_back = 1;
         return BPE_OK;
     }
-    if (*written + total > cap) return fail(h, BPE_ERR_CAPACITY, "output buffer too small");
+    if (*written + total > cap) {
+        if (e0) { cudaEventDestroy(e0); cudaEventDestroy(e1); }
+        return fail(h, BPE_ERR_CAPACITY, "output buffer too small");
+    }
     if (total > S->ids_cap) {
         cudaFree(S->d_ids); S->d_ids = nullptr; S->ids_cap = 0;
         const u64 want = total + total / 8 + 1024;
@@ -431,7 +435,7 @@ static int encode_with_offsets(bpe_handle *h, const uint8_t *bytes, uint64_t n, 
     return BPE_OK;
 }
 
-extern "C" int bpe_encode_stats(bpe_handle *h, uint64_t *out /* [8] */) {
+extern "C" int bpe_encode_stats(bpe_handle *h, uint64_t *out /* [10] */) {
     if (!h || !out) return BPE_ERR_ARG;
     memset(out, 0, 10 * sizeof(uint64_t));
     if (!h->enc) return BPE_OK;

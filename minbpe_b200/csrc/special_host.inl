@@ -49,11 +49,11 @@ static int spec_set(bpe_handle *h, const uint8_t *bytes, const uint32_t *offsets
         hash = spec_fnv(ids, (size_t)k * 4, hash) | 1ull;
     }
     if (hash == S->hash && k == S->k) return BPE_OK;
-    S->k = k; S->hash = hash;
+    S->k = k; S->hash = 0;                              // becomes `hash` once the device copies are in place
     S->blob.assign(bytes, bytes + (k ? offsets[k] : 0));
     S->off.assign(offsets, offsets + (k ? k + 1 : 0));
     S->ids.assign(ids, ids + k);
-    if (!k) return BPE_OK;
+    if (!k) return BPE_OK;                              // k == 0 <=> hash == 0
     if (!S->d_blob) {
         CU(cudaMalloc(&S->d_blob, SPEC_MAX * SPEC_MAX_LEN));
         CU(cudaMalloc(&S->d_off, (SPEC_MAX + 1) * 4));
@@ -69,6 +69,7 @@ static int spec_set(bpe_handle *h, const uint8_t *bytes, const uint32_t *offsets
     CU(cudaMemcpyAsync(S->d_ids, S->ids.data(), (size_t)k * 4, cudaMemcpyHostToDevice, h->stream));
     CU(cudaMemcpyAsync(S->d_first, first, sizeof(first), cudaMemcpyHostToDevice, h->stream));
     CU(cudaStreamSynchronize(h->stream));   // `first` is a stack buffer
+    S->hash = hash;
     return BPE_OK;
 }
 
