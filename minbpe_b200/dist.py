@@ -310,10 +310,12 @@ def encode_file(engine, path, merges, byte_perm=None, specials=None, group=None,
         """does the cut between bytes p-1 and p fall strictly inside an occurrence of a special token?"""
         return any(raw[p - j: p - j + len(t)] == t for t in toks for j in range(1, len(t)) if p - j >= 0)
 
-    def safe(window):
-        """first letter+space cut of the window that does not lie inside an occurrence of a special token, or -1"""
+    back = max((len(t) for t in toks), default=0)       # an occurrence that covers a cut starts less than this before it
+
+    def safe(window, base):
+        """first letter+space cut at or after window[base] that does not lie inside an occurrence of a special token, or -1"""
         w = np.asarray(window, dtype=np.uint8)
-        raw, base = w.tobytes(), 0
+        raw = w.tobytes()
         while True:
             p = first_safe_cut(w[base:])
             if p < 0:
@@ -329,10 +331,11 @@ def encode_file(engine, path, merges, byte_perm=None, specials=None, group=None,
         if r >= world:
             return size
         lo = size * r // world
-        p = safe(mm[lo: min(size, lo + (1 << 20))])
+        w0 = max(0, lo - back)                          # the window starts early enough to see a special that straddles `lo`
+        p = safe(mm[w0: min(size, lo + (1 << 20))], lo - w0)
         if p < 0:
             raise ValueError(f"no usable letter+space cut point in the MiB after offset {lo}: cannot shard this text")
-        return lo + p
+        return w0 + p
     lo, hi = cut(rank), cut(rank + 1)
     ids = engine.encode_text_gpt4(mm[lo:hi], merges, byte_perm, specials=specials) if hi > lo else np.zeros(0, np.int32)
     if not gather:

@@ -146,3 +146,29 @@ def test_synthetic_shards_are_ranges_of_one_corpus():
     for p in parts:
         p.tobytes().decode("utf-8")
     assert not np.array_equal(parts[0], parts[1])
+
+
+def test_encode_file_cuts_never_fall_inside_a_special_token(tmp_path):
+    """dist.encode_file: a rank's byte range ends at a letter+space point that is not inside an occurrence of a special
+    token — also when the occurrence straddles the nominal cut (size * r // world), i.e. starts before the search window."""
+    import numpy as np
+    from minbpe_b200.dist import encode_file
+
+    class Ranges:   # stands in for the engine: "ids" = the bytes it was handed
+        def encode_text_gpt4(self, raw, merges, perm, specials=None):
+            return np.asarray(raw, dtype=np.uint8).astype(np.int32)
+
+    sp = b"<|end a of b text c|>"          # letter+space points inside the token
+    for shift in range(len(sp) + 2):
+        tail = b" tail word" * 120
+        head = b"xy" * ((len(tail) + len(sp)) // 2 + 8)
+        text = head[: len(tail) + shift] + sp + tail          # nominal cut of world 2 walks through the token as shift grows
+        p = tmp_path / f"t{shift}.txt"
+        p.write_bytes(text)
+        for world in (2, 3):
+            parts = [encode_file(Ranges(), str(p), None, None, [(sp, 1000)], rank=r, world=world) for r in range(world)]
+            assert np.concatenate(parts).astype(np.uint8).tobytes() == text
+            at = text.find(sp)
+            for c in np.cumsum([len(x) for x in parts])[:-1]:
+                assert not (at < c < at + len(sp)), (shift, world, int(c), at)
+                assert text[c - 1: c].isalpha() and text[c: c + 1] == b" "
