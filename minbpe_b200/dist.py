@@ -255,7 +255,8 @@ def train_file(engine, device, path, num_merges, first_idx=256, group=None, poll
     """regex.py:36-66 for a text FILE that may be far larger than one GPU call: every rank maps the file, takes
     its byte range (shard_byte_range: cuts at letter+space), uploads it — bpe_load_text_gpt4 splits it on the device
     in pieces — and the ranks train together (ShardedTrainer).  Without an initialised process group (or with one
-    rank) the whole file goes to this GPU and the device-driven loop (bpe_train) runs.  GPT-4 split pattern only.
+    rank) the whole file goes to this GPU and the device-driven loop (bpe_train) runs.  The split pattern is the engine's
+    current one (BPE_OPT_SPLIT_PATTERN: GPT-4 by default, GPT-2 selectable).
     Returns (pairs, counts, n_done), identical on every rank."""
     size = os.path.getsize(path)
     mm = np.memmap(path, dtype=np.uint8, mode="r") if size else np.zeros(0, dtype=np.uint8)

@@ -347,7 +347,7 @@ class RegexTokenizer(Tokenizer):
         """train() for a UTF-8 text file of any size (not in the reference, which takes a str: regex.py:36).  The file
         is memory-mapped and split on the device in pieces; when torch.distributed is initialised (one process per
         GPU) every rank trains on its own byte range — cut where a letter is followed by a space, a provable chunk
-        boundary — and all ranks end with identical merges / vocab.  GPT-4 split pattern only."""
+        boundary of both patterns — and all ranks end with identical merges / vocab.  GPT-2 / GPT-4 split patterns only."""
         assert vocab_size >= 256
         which = self._DEVICE_PATTERNS.get(self.compiled_pattern.pattern)
         if which is None:
