@@ -29,11 +29,13 @@
 
 struct EncState;
 struct SpecSet;
+struct GenEnc;
 struct bpe_handle {
     int device = 0;
     EncState *enc = nullptr;          // memoised chunk encode (encode2_host.inl): rank table, memo, id pool, scratch
     bpe_handle *enc_scratch = nullptr;   // general encode path (encode_host.inl) works on its own stream buffers
     SpecSet *spec = nullptr;             // special tokens of the current encode call (special_host.inl)
+    GenEnc *gen = nullptr;               // general encode path: device scratch + the rank table of the last merges seen (encode_host.inl)
     int sms = 0;
     cudaStream_t stream = nullptr;       // the stream every kernel of this handle runs on
     cudaStream_t own_stream = nullptr;   // created by bpe_create; `stream` may point at a caller's stream instead
@@ -93,6 +95,7 @@ static thread_local std::string g_create_err;
 static void xchg_release(bpe_handle *h);
 static void enc2_free(bpe_handle *h);
 static void spec_free(bpe_handle *h);
+static void gen_free(bpe_handle *h);
 static u64 g_split_piece_override = 0;   // BPE_OPT_SPLIT_PIECE (test hook): bytes per piece of the device splitter
 
 static int fail(bpe_handle *h, int code, const std::string &msg) {
@@ -221,6 +224,7 @@ extern "C" int bpe_destroy(bpe_handle *h) {
     xchg_release(h);
     enc2_free(h);
     spec_free(h);
+    gen_free(h);
     if (h->enc_scratch) bpe_destroy(h->enc_scratch);
     if (h->split_slab) cudaFree(h->split_slab);
     if (h->ctl) cudaFree(h->ctl);
