@@ -69,6 +69,9 @@ def jobs():
                                     cwd=ROOT, env=_env(lib), stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True),
     }
     procs["filter"] = _pytest(lib, [t("test_gpu_zz_filter.py")], order="random")
+    # __graft_entry__.smoke(), the call the driver makes on cuda:0 before the bench
+    procs["smoke"] = subprocess.Popen([sys.executable, "-c", "import __graft_entry__ as g; g.smoke()"], cwd=ROOT, env=_env(lib),
+                                      stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
     procs["fuzz"] = subprocess.Popen([sys.executable, os.path.join(EMU, "emu_fuzz_encode.py"), "120", "7"], cwd=ROOT, env=_env(lib),
                                      stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
     bench_args = ["--size-mib", "1", "--steps", "6", "--warmup", "3", "--strong-mib", "2", "--strong-sparse-at", "24", "--strong-check", "16",
@@ -121,6 +124,10 @@ def test_emu_sharded_loop_collective_and_p2p(jobs):
 def test_emu_segment_filter_training(jobs):
     out = _finish(jobs, "filter")
     assert " passed" in out and "failed" not in out
+
+
+def test_emu_smoke_entry_point(jobs):
+    assert "smoke ok" in _finish(jobs, "smoke")
 
 
 def test_emu_encode_fuzz_under_guard_pages(jobs):
