@@ -231,14 +231,36 @@ static void run_block(Sched *s, const LaunchCfg &cfg, dim3 bid) {
 static std::mutex g_trace_mu;
 static std::map<std::string, unsigned long long> g_trace;
 
-void launch(const LaunchCfg &cfg, const char *kernel, const std::function<void()> &body) {
+static std::map<const void *, int> g_dyn_smem;      // opt-in dynamic shared memory per kernel (default limit: 48 KB)
+void set_max_dyn_smem(const void *func, int bytes) {
+    std::lock_guard<std::mutex> lk(g_trace_mu);
+    g_dyn_smem[func] = bytes;
+}
+
+void launch(const LaunchCfg &cfg, const char *kernel, const void *func, const std::function<void()> &body) {
+    int smem_limit = 48 * 1024;
     {
         std::lock_guard<std::mutex> lk(g_trace_mu);
         g_trace[kernel] += 1;
+        auto it = g_dyn_smem.find(func);
+        if (it != g_dyn_smem.end() && it->second > smem_limit) smem_limit = it->second;
     }
     Sched *s = sched();
     const unsigned n = cfg.block.x * cfg.block.y * cfg.block.z;
     if (n == 0 || n > MAX_THREADS) { fprintf(stderr, "emu: bad block size %u\n", n); abort(); }
+    // what the CUDA runtime rejects with "invalid configuration argument" / "invalid argument" (it would surface as a
+    // failed launch on the GPU; here it stops the test)
+    if (cfg.grid.x == 0 || cfg.grid.y == 0 || cfg.grid.z == 0 || cfg.grid.x > 0x7fffffffu || cfg.grid.y > 65535u || cfg.grid.z > 65535u ||
+        cfg.block.z > 64u) {
+        fprintf(stderr, "emu: invalid launch configuration of %s: grid (%u,%u,%u) block (%u,%u,%u)\n", kernel, cfg.grid.x, cfg.grid.y,
+                cfg.grid.z, cfg.block.x, cfg.block.y, cfg.block.z);
+        abort();
+    }
+    if (cfg.smem > (size_t)smem_limit) {
+        fprintf(stderr, "emu: %s launched with %zu bytes of dynamic shared memory, limit %d (cudaFuncSetAttribute missing?)\n", kernel,
+                cfg.smem, smem_limit);
+        abort();
+    }
     if (s->in_kernel) { fprintf(stderr, "emu: nested launch\n"); abort(); }
     if (cfg.smem > s->dyn_cap) {
         free(s->dyn);

@@ -71,7 +71,8 @@ struct LaunchCfg {
     dim3 grid, block; size_t smem; void *stream;
     LaunchCfg(dim3 g, dim3 b, size_t s = 0, void *st = nullptr) : grid(g), block(b), smem(s), stream(st) {}
 };
-void launch(const LaunchCfg &cfg, const char *kernel, const std::function<void()> &body);
+void launch(const LaunchCfg &cfg, const char *kernel, const void *func, const std::function<void()> &body);
+void set_max_dyn_smem(const void *func, int bytes);   // cudaFuncSetAttribute(MaxDynamicSharedMemorySize)
 }  // namespace emu
 // names of the kernels launched by this process since the last call, one per line (tests/emu/kernel_coverage.py)
 extern "C" size_t emu_kernel_trace(char *buf, size_t cap);
@@ -82,7 +83,7 @@ extern "C" size_t emu_kernel_trace(char *buf, size_t cap);
 #define EMU_UNPAREN(...) __VA_ARGS__
 #define EMU_STR2(...) #__VA_ARGS__
 #define EMU_STR(...) EMU_STR2(__VA_ARGS__)
-#define EMU_LAUNCH(K, CFG, ARGS) emu::launch(emu::LaunchCfg CFG, EMU_STR(EMU_UNPAREN K), [&]() { EMU_UNPAREN K ARGS; })
+#define EMU_LAUNCH(K, CFG, ARGS) emu::launch(emu::LaunchCfg CFG, EMU_STR(EMU_UNPAREN K), reinterpret_cast<const void *>(&(EMU_UNPAREN K)), [&]() { EMU_UNPAREN K ARGS; })
 
 static inline void __syncthreads() { emu::sync_threads(); }
 static inline void __syncwarp(unsigned mask = 0xffffffffu) { emu::collective(emu::C_SYNC, mask, 0, 0); }
@@ -144,7 +145,7 @@ template <class T, class U, class W> static inline T atomicCAS(T *p, U cmp, W va
 
 // ---- CUDA runtime -----------------------------------------------------------------------------------------------
 typedef int cudaError_t;
-enum { cudaSuccess = 0, cudaErrorMemoryAllocation = 2, cudaErrorLaunchOutOfResources = 701 };
+enum { cudaSuccess = 0, cudaErrorInvalidValue = 1, cudaErrorMemoryAllocation = 2, cudaErrorLaunchOutOfResources = 701 };
 enum cudaMemcpyKind { cudaMemcpyHostToHost, cudaMemcpyHostToDevice, cudaMemcpyDeviceToHost, cudaMemcpyDeviceToDevice };
 enum { cudaStreamNonBlocking = 1, cudaIpcMemLazyEnablePeerAccess = 1 };
 enum cudaFuncAttribute { cudaFuncAttributeMaxDynamicSharedMemorySize = 8 };
@@ -181,7 +182,13 @@ cudaError_t cudaEventDestroy(cudaEvent_t e);
 cudaError_t cudaEventRecord(cudaEvent_t e, cudaStream_t = nullptr);
 static inline cudaError_t cudaEventSynchronize(cudaEvent_t) { return cudaSuccess; }
 cudaError_t cudaEventElapsedTime(float *ms, cudaEvent_t a, cudaEvent_t b);
-template <class F> static inline cudaError_t cudaFuncSetAttribute(F, cudaFuncAttribute, int) { return cudaSuccess; }
+template <class F> static inline cudaError_t cudaFuncSetAttribute(F f, cudaFuncAttribute a, int v) {
+    if (a == cudaFuncAttributeMaxDynamicSharedMemorySize) {
+        if (v > 227 * 1024) return cudaErrorInvalidValue;      // sm_100: 227 KB per CTA
+        emu::set_max_dyn_smem(reinterpret_cast<const void *>(f), v);
+    }
+    return cudaSuccess;
+}
 template <class F> static inline cudaError_t cudaOccupancyMaxActiveBlocksPerMultiprocessor(int *n, F, int, size_t) { *n = 1; return cudaSuccess; }
 static inline cudaError_t cudaIpcGetMemHandle(cudaIpcMemHandle_t *h, void *p) { memset(h, 0, sizeof(*h)); memcpy(h, &p, sizeof(p)); return cudaSuccess; }
 static inline cudaError_t cudaIpcOpenMemHandle(void **p, cudaIpcMemHandle_t h, unsigned) { memcpy(p, &h, sizeof(*p)); return cudaSuccess; }
