@@ -81,7 +81,11 @@ def build(force=False):
     # EMU_SANITIZE=1: UBSan's alignment check turns every vector access of the kernels (uint2 / uint4 / ulonglong2 loads and
     # stores carry their CUDA alignment here) into a trap when the address is not aligned as the GPU requires — x86 itself
     # would not notice.  Load the result with LD_PRELOAD=$(g++ -print-file-name=libubsan.so) under python.
-    san = ["-fsanitize=alignment", "-fno-sanitize-recover=alignment"] if os.environ.get("EMU_SANITIZE") else []
+    # Also checked: shift counts >= the operand width (x86 masks the count, the GPU's shl/shr clamp: `1u << 32` is 1 here and 0
+    # there — code that reaches such a shift computes different things on the two) and indices past the end of arrays of
+    # known size (shared-memory and local arrays).
+    checks = "alignment,shift,bounds"
+    san = [f"-fsanitize={checks}", f"-fno-sanitize-recover={checks}"] if os.environ.get("EMU_SANITIZE") else []
     cmd = ["g++", "-std=c++17", opt, "-g", "-fPIC", "-shared", "-fno-strict-aliasing", "-Wno-unknown-pragmas", "-Wno-attributes"] + san + [
            "-I", HERE, "-I", os.path.join(ROOT, "include"), "-I", os.path.join(OUT, "src"),
            os.path.join(OUT, "src", "b200bpe_emu.cpp"), os.path.join(HERE, "cuda_emu.cpp"), "-o", LIB, "-lpthread"]
