@@ -74,6 +74,9 @@ def jobs():
                                       stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
     procs["fuzz"] = subprocess.Popen([sys.executable, os.path.join(EMU, "emu_fuzz_encode.py"), "120", "7"], cwd=ROOT, env=_env(lib),
                                      stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
+    # special-token front end (device) against the unmodified reference class (oracle/_ref, vendored by __graft_entry__.build())
+    procs["fuzz_special"] = subprocess.Popen([sys.executable, os.path.join(EMU, "emu_fuzz_special.py"), "100", "5"], cwd=ROOT, env=_env(lib),
+                                             stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
     bench_args = ["--size-mib", "1", "--steps", "6", "--warmup", "3", "--strong-mib", "2", "--strong-sparse-at", "24", "--strong-check", "16",
                   "--encode-gb", "0.002", "--encode-merges", "200", "--encode-train-mib", "1", "--leg-budget-s", "600"]
     benv = dict(_env(lib), BPE_BENCH_EMU="1")
@@ -132,6 +135,14 @@ def test_emu_smoke_entry_point(jobs):
 
 def test_emu_encode_fuzz_under_guard_pages(jobs):
     assert "emu fuzz encode ok" in _finish(jobs, "fuzz")
+
+
+def test_emu_special_tokens_fuzz_against_the_reference_class(jobs):
+    p = jobs["fuzz_special"]
+    out, _ = p.communicate(timeout=1500)
+    if p.returncode == 2:
+        pytest.skip("oracle/_ref is not vendored in this checkout (needs /root/reference once: __graft_entry__.build())")
+    assert p.returncode == 0 and "emu fuzz special ok" in out, out[-4000:]
 
 
 def _bench_line(jobs, name):
