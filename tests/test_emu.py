@@ -77,6 +77,9 @@ def jobs():
     # special-token front end (device) against the unmodified reference class (oracle/_ref, vendored by __graft_entry__.build())
     procs["fuzz_special"] = subprocess.Popen([sys.executable, os.path.join(EMU, "emu_fuzz_special.py"), "100", "5"], cwd=ROOT, env=_env(lib),
                                              stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
+    # train() / encode() / save() of the classes against the unmodified reference classes on random small texts
+    procs["fuzz_train"] = subprocess.Popen([sys.executable, os.path.join(EMU, "emu_fuzz_train_ref.py"), "100", "5"], cwd=ROOT, env=_env(lib),
+                                           stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
     bench_args = ["--size-mib", "1", "--steps", "6", "--warmup", "3", "--strong-mib", "2", "--strong-sparse-at", "24", "--strong-check", "16",
                   "--encode-gb", "0.002", "--encode-merges", "200", "--encode-train-mib", "1", "--leg-budget-s", "600"]
     benv = dict(_env(lib), BPE_BENCH_EMU="1")
@@ -143,6 +146,14 @@ def test_emu_special_tokens_fuzz_against_the_reference_class(jobs):
     if p.returncode == 2:
         pytest.skip("oracle/_ref is not vendored in this checkout (needs /root/reference once: __graft_entry__.build())")
     assert p.returncode == 0 and "emu fuzz special ok" in out, out[-4000:]
+
+
+def test_emu_train_fuzz_against_the_reference_classes(jobs):
+    p = jobs["fuzz_train"]
+    out, _ = p.communicate(timeout=1500)
+    if p.returncode == 2:
+        pytest.skip("oracle/_ref is not vendored in this checkout (needs /root/reference once: __graft_entry__.build())")
+    assert p.returncode == 0 and "emu fuzz train ok" in out, out[-4000:]
 
 
 def _bench_line(jobs, name):
