@@ -40,6 +40,29 @@ def test_split_offsets_gpt2_vs_regex(taylorswift):
     eng.close()
 
 
+def test_split_gpt2_random_adversarial():
+    """Random strings over an alphabet of the characters the two patterns treat differently (apostrophe forms in both cases,
+    digit runs, Unicode spaces and line separators, case-folding specials) — device split vs regex.findall, GPT-2 pattern."""
+    import random
+    from minbpe_b200 import engine as E
+    rnd = random.Random(2424)
+    alphabet = list("ab'sSdDmMtTlLvVeErR 12\t\n\r!.,'") + [chr(c) for c in (0x3000, 0xe9, 0x65e5, 0x17f, 0x212a, 0xbd, 0x2028, 0x85, 0xa0, 0x1f600)]
+    alphabet += [" ", " ", "  ", "\n\n", "'ll", "'ve", "'LL", " '", "123456", "x" * 7]
+    eng = E.Engine(0)
+    eng.set_option(E.OPT_SPLIT_PATTERN, 1)
+    try:
+        for size in (1, 2, 3, 17, 2047, 2048, 2049, 4097, 60000, 300000):
+            text = "".join(rnd.choice(alphabet) for _ in range(size))
+            data, offs = oracle.split_to_stream(text, GPT2)
+            assert np.array_equal(eng.split_gpt4(data.tobytes()), offs), (size, text[:80])
+        text = " " * 5000 + "a" * 7000 + "1" * 9001 + "!" * 4099 + "\n" * 3000 + " \n" * 2500 + "x" + "'s" * 3000
+        data, offs = oracle.split_to_stream(text, GPT2)
+        assert np.array_equal(eng.split_gpt4(data.tobytes()), offs)
+    finally:
+        eng.set_option(E.OPT_SPLIT_PATTERN, 0)
+        eng.close()
+
+
 def test_regex_tokenizer_with_the_gpt2_pattern(taylorswift):
     from minbpe_b200 import RegexTokenizer
     text = taylorswift                                   # 185 KB: above the device-split threshold
