@@ -221,10 +221,14 @@ extern "C" int bpe_xchg_create(bpe_handle *h, int32_t world, int32_t rank, int32
     h->xchg_bytes = bytes; h->xchg_stride = stride; h->xchg_V = (u32)vocab_cap;
     h->xargs.world = world; h->xargs.rank = rank; h->xargs.delta_stride = stride;
     h->xargs.peer[rank] = h->xchg;
-    cudaIpcMemHandle_t ipc;
-    CU(cudaIpcGetMemHandle(&ipc, h->xchg));
-    memcpy(ipc_handle_out, &ipc, 64);
-    if (world == 1) h->xchg_attached = true;
+    if (world > 1) {
+        cudaIpcMemHandle_t ipc;
+        CU(cudaIpcGetMemHandle(&ipc, h->xchg));
+        memcpy(ipc_handle_out, &ipc, 64);
+    } else {              // nobody maps the block of a single rank: no IPC needed (containers may refuse it)
+        memset(ipc_handle_out, 0, 64);
+        h->xchg_attached = true;
+    }
     return BPE_OK;
 }
 
