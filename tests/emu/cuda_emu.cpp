@@ -7,8 +7,11 @@
 #include <time.h>
 #include <unistd.h>
 
+#include <atomic>
+#include <condition_variable>
 #include <map>
 #include <mutex>
+#include <thread>
 #include <string>
 #include <vector>
 
@@ -228,6 +231,97 @@ static void run_block(Sched *s, const LaunchCfg &cfg, dim3 bid) {
     }
 }
 
+// ---- EMU_PAR=n: the blocks of a grid run on n OS threads at the same time ------------------------------------------
+// By default the blocks of a launch run one after the other, which hides every race BETWEEN blocks (a slot claimed with
+// atomicCAS and read by another block before its payload is written, list appends, tickets, look-back chains, "last block
+// out" counters).  With EMU_PAR each calling thread owns a pool of n - 1 workers; every worker has its own scheduler
+// (fibers, __shared__ storage: both thread_local) and pulls block indices from a shared counter, lowest first — the order a
+// GPU starts blocks in, so a block that waits for a lower-numbered one (decoupled look-back) always finds it started.
+static unsigned par_threads() {
+    static int v = -1;
+    if (v < 0) { const char *e = getenv("EMU_PAR"); v = e ? atoi(e) : 0; if (v < 0) v = 0; if (v > 64) v = 64; }
+    return (unsigned)v;
+}
+
+struct ParJob {
+    const LaunchCfg *cfg = nullptr;
+    const std::function<void()> *body = nullptr;
+    std::atomic<unsigned long long> next{0};
+    unsigned long long total = 0;
+};
+
+struct ParPool {
+    std::mutex mu;
+    std::condition_variable cv_go, cv_done;
+    std::vector<std::thread> workers;
+    ParJob *job = nullptr;
+    unsigned long long gen = 0;
+    unsigned running = 0;
+    bool quit = false;
+};
+
+static void par_run_blocks(Sched *s, ParJob *j) {
+    const LaunchCfg &cfg = *j->cfg;
+    if (cfg.smem > s->dyn_cap) {
+        free(s->dyn);
+        s->dyn_cap = cfg.smem + 4096;
+        if (posix_memalign(&s->dyn, 1024, s->dyn_cap)) abort();
+    }
+    s->body = j->body;
+    s->in_kernel = true;
+    s->spins = 0;
+    for (;;) {
+        const unsigned long long b = j->next.fetch_add(1);
+        if (b >= j->total) break;
+        const unsigned x = (unsigned)(b % cfg.grid.x), y = (unsigned)((b / cfg.grid.x) % cfg.grid.y), z = (unsigned)(b / ((unsigned long long)cfg.grid.x * cfg.grid.y));
+        if (s->dyn) memset(s->dyn, 0xCD, cfg.smem);
+        run_block(s, cfg, dim3(x, y, z));
+    }
+    s->in_kernel = false;
+    s->cur = nullptr;
+}
+
+static void par_worker(ParPool *p) {
+    Sched *s = sched();
+    unsigned long long seen = 0;
+    for (;;) {
+        ParJob *j;
+        {
+            std::unique_lock<std::mutex> lk(p->mu);
+            p->cv_go.wait(lk, [&] { return p->quit || p->gen != seen; });
+            if (p->quit) return;
+            seen = p->gen;
+            j = p->job;
+        }
+        par_run_blocks(s, j);
+        {
+            std::lock_guard<std::mutex> lk(p->mu);
+            if (--p->running == 0) p->cv_done.notify_all();
+        }
+    }
+}
+
+static void launch_parallel(Sched *s, const LaunchCfg &cfg, const std::function<void()> &body, unsigned long long nblocks, unsigned par) {
+    static thread_local ParPool *pool = nullptr;      // one pool per calling thread (= per emulated GPU); lives as long as the process
+    if (!pool) {
+        pool = new ParPool();
+        for (unsigned i = 1; i < par; ++i) pool->workers.emplace_back(par_worker, pool);
+    }
+    ParJob job;
+    job.cfg = &cfg; job.body = &body; job.total = nblocks;
+    {
+        std::lock_guard<std::mutex> lk(pool->mu);
+        pool->job = &job;
+        pool->running = (unsigned)pool->workers.size();
+        pool->gen++;
+    }
+    pool->cv_go.notify_all();
+    par_run_blocks(s, &job);                          // the calling thread works too
+    std::unique_lock<std::mutex> lk(pool->mu);
+    pool->cv_done.wait(lk, [&] { return pool->running == 0; });
+    pool->job = nullptr;
+}
+
 static std::mutex g_trace_mu;
 static std::map<std::string, unsigned long long> g_trace;
 
@@ -267,6 +361,9 @@ void launch(const LaunchCfg &cfg, const char *kernel, const void *func, const st
         s->dyn_cap = cfg.smem + 4096;
         if (posix_memalign(&s->dyn, 1024, s->dyn_cap)) abort();
     }
+    const unsigned long long nblocks = (unsigned long long)cfg.grid.x * cfg.grid.y * cfg.grid.z;
+    const unsigned par = par_threads();
+    if (par > 1 && nblocks > 1) { launch_parallel(s, cfg, body, nblocks, par); return; }
     s->body = &body;
     s->in_kernel = true;
     s->spins = 0;

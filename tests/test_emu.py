@@ -39,13 +39,15 @@ def _env(lib):
     return env
 
 
-def _pytest(lib, files, k=None, order=None):
+def _pytest(lib, files, k=None, order=None, par=None):
     cmd = [sys.executable, "-m", "pytest", "-x", "-q", "-m", "gpu", "-p", "no:cacheprovider", "-o", "timeout=900"] + files
     if k:
         cmd += ["-k", k]
     env = _env(lib)
     if order:        # thread interleaving of the emulator (by index / reverse / random): a kernel that cares has a data race
         env["EMU_ORDER"] = order
+    if par:          # the blocks of a grid on `par` OS threads at the same time: races BETWEEN blocks (atomics, claims, look-back)
+        env["EMU_PAR"] = str(par)
     return subprocess.Popen(cmd, cwd=ROOT, env=env, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
 
 
@@ -59,7 +61,7 @@ def jobs():
         # round-2 kernels that have not run on a GPU yet — memoised chunk encode (k_encode2.cuh), bpe_replay / resume, the
         # special-token front end (k_special.cuh), file / shard entry points — and bpe_decode
         "new_kernels": _pytest(lib, [t("test_gpu_zy_encode2.py"), t("test_gpu_zz_resume.py"), t("test_gpu_zz_file.py"), t("test_gpu_zz_special.py"), t("test_gpu_zz_gpt2.py"), t("test_gpu_zz_gpt4.py"), t("test_gpu_zz_hist.py"), t("test_gpu_zz_golden_r2.py"),
-                                       t("test_gpu_decode.py")], order="random"),
+                                       t("test_gpu_decode.py")], order="random", par=3),
         # kernels already validated on B200s, as a check of the emulator itself (golden vectors of the reference)
         "validated_kernels": _pytest(lib, [t("test_gpu_parity.py")],
                                      "wikipedia or taylorswift or small_cases or primitives or long_runs or table_growth or rescan"),
@@ -68,11 +70,11 @@ def jobs():
         "sharded": subprocess.Popen([sys.executable, os.path.join(EMU, "emu_sharded.py"), "2:collective", "2:p2p", "3:p2p", "4:p2p"],
                                     cwd=ROOT, env=_env(lib), stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True),
     }
-    procs["filter"] = _pytest(lib, [t("test_gpu_zz_filter.py")], order="random")
+    procs["filter"] = _pytest(lib, [t("test_gpu_zz_filter.py")], order="random", par=3)
     # __graft_entry__.smoke(), the call the driver makes on cuda:0 before the bench
     procs["smoke"] = subprocess.Popen([sys.executable, "-c", "import __graft_entry__ as g; g.smoke()"], cwd=ROOT, env=_env(lib),
                                       stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
-    procs["fuzz"] = subprocess.Popen([sys.executable, os.path.join(EMU, "emu_fuzz_encode.py"), "120", "7"], cwd=ROOT, env=_env(lib),
+    procs["fuzz"] = subprocess.Popen([sys.executable, os.path.join(EMU, "emu_fuzz_encode.py"), "120", "7"], cwd=ROOT, env=dict(_env(lib), EMU_PAR="3"),
                                      stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
     # special-token front end (device) against the unmodified reference class (oracle/_ref, vendored by __graft_entry__.build())
     procs["fuzz_special"] = subprocess.Popen([sys.executable, os.path.join(EMU, "emu_fuzz_special.py"), "100", "5"], cwd=ROOT, env=_env(lib),
