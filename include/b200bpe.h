@@ -214,7 +214,7 @@ int bpe_decode(bpe_handle *h, const int32_t *ids, uint64_t n_ids, const uint8_t 
  *     bpe_step_begin, all-reduce of the 65536-bin histogram (once), bpe_step_table         (as above)
  *     bpe_step_fused(n) ... bpe_step_poll ... bpe_step_result
  * vocab_cap must equal first_idx + num_merges of bpe_step_table.  world <= 16, one process per GPU on one
- * NVLink box (peer access required).  world == 1 works without peers (tests). */
+ * NVLink box (peer access required).  world == 1 works without peers and without CUDA IPC (the handle is zeroed). */
 int bpe_xchg_create(bpe_handle *h, int32_t world, int32_t rank, int32_t vocab_cap, uint8_t *ipc_handle_out /* [64] */);
 int bpe_xchg_attach(bpe_handle *h, const uint8_t *all_handles /* [world][64], own slot ignored */);
 /* Handshake over the mapped blocks (every rank calls it): push a flag to every peer, wait for theirs, pull a magic
