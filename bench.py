@@ -335,6 +335,50 @@ def python_reference_run(raw, nbytes=1 << 20, merges=8):
             "sample": f"karpathy/minbpe RegexTokenizer.train (pure Python, incl. its regex split) on the first {cut} bytes, {merges} merges"}
 
 
+def _taylorswift():
+    with open(os.path.join(ROOT, "tests", "golden", "taylorswift.txt"), encoding="utf-8") as f:
+        return f.read()
+
+
+def cfg2_reference():
+    """BASELINE configs[1] (cfg2) with the UNMODIFIED reference classes (oracle/_ref): BasicTokenizer and RegexTokenizer
+    .train(taylorswift, 512), what the reference's train.py does — pure Python, one core.  None when not vendored."""
+    from oracle import make_ref
+    ref = make_ref.load()
+    if ref is None:
+        return None
+    text, out = _taylorswift(), {}
+    for name, cls in (("basic", ref.BasicTokenizer), ("regex", ref.RegexTokenizer)):
+        tok = cls()
+        t0 = time.perf_counter()
+        tok.train(text, 512)
+        out[name + "_seconds"] = time.perf_counter() - t0
+        out[name + "_merges_sha16"] = merges_sha(np.array(list(tok.merges), dtype=np.int32))
+    out["what"] = "karpathy/minbpe {Basic,Regex}Tokenizer.train(tests/taylorswift.txt, 512), unmodified pure Python, 1 core"
+    return out
+
+
+def cfg2_leg(device):
+    """The same two calls through the product classes (minbpe_b200.BasicTokenizer / RegexTokenizer over the C ABI): text in,
+    merges + vocab out, wall clock, median of 3; merges compared with the golden vectors the reference produced."""
+    from minbpe_b200 import BasicTokenizer, RegexTokenizer
+    text, out = _taylorswift(), {}
+    golden = json.load(open(os.path.join(ROOT, "tests", "golden", "golden_train.json")))
+    for name, cls in (("basic", BasicTokenizer), ("regex", RegexTokenizer)):
+        tok = cls(device=device)
+        tok.train(text, 300)                 # warm-up: handle, class tables, allocations
+        runs = []
+        for _ in range(3):
+            t0 = time.perf_counter()
+            tok.train(text, 512)
+            runs.append(time.perf_counter() - t0)
+        out[name + "_seconds"] = sorted(runs)[1]
+        out[name + "_merges_sha16"] = merges_sha(np.array(list(tok.merges), dtype=np.int32))
+        out[name + "_equals_reference_golden"] = [list(p) for p in tok.merges] == golden[f"taylorswift_{name}_512"]["merges"]
+    out["what"] = "minbpe_b200.{Basic,Regex}Tokenizer.train(tests/golden/taylorswift.txt, 512): str in, merges + vocab out, wall clock, median of 3"
+    return out
+
+
 def _ref_worker(args):
     seed, shard, nbytes, steps, warmup = args
     from minbpe_b200.presplit import chunk_offsets_1proc
@@ -386,7 +430,8 @@ def run_reference(args):
         "merges_per_s": merges_per_s,
         "cpu_baseline": {"value": value, "unit": "GB/s", "cores": cores, "kind": "port", "sample": sample,
                          "passes_GBps": [p[0] for p in passes], "one_replica_GBps": solo_rate,
-                         "parallel_efficiency": value / (solo_rate * cores), "python_reference": pyref},
+                         "parallel_efficiency": value / (solo_rate * cores), "python_reference": pyref,
+                         "cfg2_reference": None if args.no_cfg2 else cfg2_reference()},
         "e2e": {"value": value, "unit": "GB/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
     print(json.dumps(line), flush=True)
@@ -1112,7 +1157,7 @@ def run_ours(args):
                      "peak_source": peak_src, "bytes_per_launch": (4.0 * n_in + 4.0 * n_out) / K, "ms_per_launch": k_ms,
                      "loop_frac_in_kernel": tm["merge_kernel_ms"] / tm["loop_ms"]},
         "cpu_baseline": cpu,
-        "full_run": None, "strong_cfg4": None, "encode_cfg5": None, "full_run_filtered": None, "hist_packed": None,
+        "cfg2": None, "full_run": None, "strong_cfg4": None, "encode_cfg5": None, "full_run_filtered": None, "hist_packed": None,
         "e2e": {"value": size * (W + K) / t_e2e / 1e9, "unit": "GB/s", "h2d_bytes_per_step": h2d / (W + K),
                 "d2h_bytes_per_step": d2h / (W + K), "seconds": t_e2e, "merges": W + K,
                 "load_seconds": t_load, "runs_seconds": [r[0] for r in e2e_runs], "host_buffer": "pinned (cudaHostRegister)" if pinned else "pageable",
@@ -1126,6 +1171,8 @@ def run_ours(args):
     dog.arm(line)
     if pinned:
         unpin_host(raw)      # nothing below reads `raw` by DMA again; later legs pin their own buffers
+    if not args.no_cfg2:
+        line["cfg2"] = guarded("cfg2", cfg2_leg, local)
     full_pairs = None
     if args.full_merges > 0:
         r = guarded("full_run", full_run, eng, raw, offs, args.full_merges, not args.no_cpu_baseline)
@@ -1242,6 +1289,7 @@ def main():
                     help="wall-clock budget of the optional legs (whole-loop run, cfg4, cfg5) after the contract line is complete; "
                          "when it runs out the line is printed with the legs finished so far")
     ap.add_argument("--no-hist-leg", action="store_true", help="skip the hist_packed leg (N=1)")
+    ap.add_argument("--no-cfg2", action="store_true", help="skip the cfg2 leg (taylorswift, vocab 512, both tokenizers through the classes)")
     ap.add_argument("--no-p2p-trial", action="store_true", help="N>1: skip the trial of the NVLink peer-memory exchange kernels")
     ap.add_argument("--no-filter-leg", action="store_true", help="skip the full_run_filtered leg (N=1)")
     ap.add_argument("--extras", action="store_true", help="side measurements (cfg2 wall time, encode throughput)")

@@ -183,6 +183,7 @@ def test_emu_bench_one_rank_every_leg(jobs):
     assert d["n_gpus"] == 1 and d["steps"] == 6 and d["gpu_launches"] > 0 and "workload" in d["config"]
     assert d["e2e"]["h2d_bytes_per_step"] > 0 and d["cpu_baseline"]["kind"] == "port"
     assert d["full_run"]["parity_all_merges"] is True and d["full_run"]["merges"] == 40
+    assert d["cfg2"]["basic_equals_reference_golden"] is True and d["cfg2"]["regex_equals_reference_golden"] is True
     assert d["strong_cfg4"]["parity_vs_oracle"]["equal"] is True
     assert d["encode_cfg5"]["parity"]["equal"] is True and d["encode_cfg5"]["memo"]["fallback_pieces"] == 0
     assert d["hist_packed"]["same_merges"] is True and d["e2e"]["hist_kernel"] == "k_hist_dense"
